@@ -1,0 +1,184 @@
+/* rpx.h — C ABI of the B200-native premise-retrieval engine (librpx.so).
+ *
+ * The reference (lean-dojo/ReProver) has NO plugin / operator / FFI interface for
+ * this path: its seam is the Python attribute surface of `PremiseRetriever`
+ * (retrieval/model.py:29) and `Corpus.get_nearest_premises` (common.py:299).  Each
+ * entry point below therefore cites the reference Python call it replaces; the
+ * Python shim `reprover_b200.retriever.B200PremiseRetriever` re-creates the
+ * reference surface on top of these calls.
+ *
+ * Conventions
+ *   - extern "C", plain pointers / integers, no torch types, no C++ exceptions.
+ *   - Every function returning `int` returns RPX_OK (0) or an RPX_ERR_* code; the
+ *     message is available from rpx_last_error() (thread-local).
+ *   - `d_` parameters are DEVICE pointers, `h_` parameters are HOST pointers.  The
+ *     caller owns every buffer; the library borrows them for the duration of the
+ *     stream-ordered work it enqueues and never frees them.  The only memory the
+ *     library uses beyond its arguments is the explicit workspace / packed-weight
+ *     buffers whose sizes it reports.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued on it;
+ *     functions return without synchronising unless stated.
+ *   - Handles are not thread-safe per handle; distinct handles are independent.
+ *   - sm_100a (B200) only.  There is no CPU or other-GPU fallback: calling a
+ *     compute entry point without such a device fails with RPX_ERR_CUDA /
+ *     RPX_ERR_UNSUPPORTED.
+ */
+#ifndef RPX_H_
+#define RPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPX_VERSION 100 /* 0.1.0 */
+
+enum {
+  RPX_OK = 0,
+  RPX_ERR_INVALID = 1,     /* bad argument */
+  RPX_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed */
+  RPX_ERR_UNSUPPORTED = 3, /* valid request outside what the engine implements */
+  RPX_ERR_WORKSPACE = 4,   /* workspace / packed buffer too small */
+  RPX_ERR_MASK = 5         /* attention_mask is not a right-padded prefix mask */
+};
+
+enum { RPX_DTYPE_BF16 = 0, RPX_DTYPE_F32 = 1 };
+
+/* Last error message of the calling thread ("" if none). */
+const char* rpx_last_error(void);
+int rpx_version(void);
+/* RPX_OK iff the current CUDA device is compute capability 10.x. */
+int rpx_device_check(void);
+
+/* ------------------------------------------------------------------------- encoder
+ * Replaces the HF `T5EncoderModel` forward that `PremiseRetriever._encode`
+ * (retrieval/model.py:92-114) calls at :101-105, plus the masked mean-pool and
+ * F.normalize at :108-114.  Architecture constants come from the checkpoint's
+ * config.json (HF T5Config; ByT5-small values in SURVEY.md §8).
+ */
+typedef struct {
+  int32_t vocab_size;       /* 384  */
+  int32_t d_model;          /* 1472 */
+  int32_t d_kv;             /* 64   */
+  int32_t d_ff;             /* 3584 */
+  int32_t num_layers;       /* 12   */
+  int32_t num_heads;        /* 6    */
+  int32_t rel_buckets;      /* 32   */
+  int32_t rel_max_distance; /* 128  */
+  float ln_eps;             /* 1e-6 */
+} rpx_t5_config;
+
+/* Raw HF weights, fp32, row-major, DEVICE pointers.  The per-layer members are
+ * HOST arrays of `num_layers` device pointers.  Safetensors key for each member
+ * is given on the right (i = layer). */
+typedef struct {
+  const float* d_shared;         /* shared.weight                                   [vocab, d_model]   */
+  const float* d_rel_bias;       /* encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight [buckets, heads] */
+  const float* d_final_ln;       /* encoder.final_layer_norm.weight                 [d_model]          */
+  const float* const* h_q;       /* encoder.block.i.layer.0.SelfAttention.q.weight  [heads*d_kv, d_model] */
+  const float* const* h_k;       /* ...k.weight                                                         */
+  const float* const* h_v;       /* ...v.weight                                                         */
+  const float* const* h_o;       /* ...o.weight                                     [d_model, heads*d_kv] */
+  const float* const* h_ln0;     /* encoder.block.i.layer.0.layer_norm.weight       [d_model]          */
+  const float* const* h_wi0;     /* encoder.block.i.layer.1.DenseReluDense.wi_0.weight [d_ff, d_model]  */
+  const float* const* h_wi1;     /* ...wi_1.weight                                                      */
+  const float* const* h_wo;      /* ...wo.weight                                    [d_model, d_ff]    */
+  const float* const* h_ln1;     /* encoder.block.i.layer.1.layer_norm.weight       [d_model]          */
+} rpx_t5_weights;
+
+typedef struct rpx_encoder rpx_encoder; /* opaque */
+
+/* Bytes of device memory the packed (bf16, RMSNorm-folded, FFN-interleaved)
+ * weight image needs; the caller allocates it and keeps it alive while the
+ * handle lives. */
+size_t rpx_encoder_packed_bytes(const rpx_t5_config* cfg);
+
+/* Builds the packed weight image on `stream` and returns a handle.
+ * Mirrors `PremiseRetriever.load_hf` (retrieval/model.py:52-66) for the encoder
+ * part: fp32 checkpoint -> bf16 compute copy. */
+int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* d_packed,
+                       size_t packed_bytes, void* stream, rpx_encoder** out);
+int rpx_encoder_destroy(rpx_encoder* enc);
+
+/* Workspace needed to encode up to `max_tokens` packed tokens in `max_seqs`
+ * sequences in one call. */
+size_t rpx_encoder_workspace_bytes(const rpx_encoder* enc, int64_t max_tokens, int64_t max_seqs);
+
+/* Tokenise + encode + pool + normalise `n_seqs` byte strings.
+ * Replaces, per batch, the tokenizer call at retrieval/model.py:199-205 (ByT5:
+ * id = byte + 3, EOS = 1 appended, truncation to max_seq_len INCLUDING the EOS;
+ * HF tokenization_byt5.py:195-208) followed by `_encode` (:92-114).
+ *   d_bytes     concatenated UTF-8 bytes of all sequences (device)
+ *   h_offsets   n_seqs + 1 byte offsets into d_bytes (HOST; the host needs the
+ *               lengths to size the launch)
+ *   d_out       [n_seqs, d_model] unit-norm rows, RPX_DTYPE_BF16 or RPX_DTYPE_F32
+ * Strings must not contain ByT5 special-token literals ("</s>", "<pad>", "<unk>",
+ * "<extra_id_N>"); callers route those through rpx_encode_ids (the Python shim does). */
+int rpx_encode_bytes(rpx_encoder* enc, const uint8_t* d_bytes, const int64_t* h_offsets,
+                     int32_t n_seqs, int32_t max_seq_len, void* d_out, int32_t out_dtype,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Exact `_encode(input_ids, attention_mask)` signature (retrieval/model.py:92-94):
+ * int64 [B, L] ids and mask on the device.  The mask must be a right-padded
+ * prefix mask with at least one token per row (what the reference tokenizer call
+ * produces); anything else returns RPX_ERR_MASK.  Synchronises `stream` once
+ * (row lengths are read back to size the launch). */
+int rpx_encode_ids(rpx_encoder* enc, const int64_t* d_input_ids, const int64_t* d_attention_mask,
+                   int32_t batch, int32_t seq_len, void* d_out, int32_t out_dtype,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Debug / parity hook: when non-NULL, every encode call also writes the fp32
+ * residual stream after the embedding and after each block to
+ * d_hidden[(layer) * n_tokens * d_model ...] (num_layers + 1 slabs, packed tokens). */
+int rpx_encoder_set_debug_hidden(rpx_encoder* enc, float* d_hidden);
+
+/* Per-kernel-class device timing (CUDA events on the launch stream).  Classes:
+ * 0 embed, 1 qkv gemm, 2 attention, 3 o-proj gemm, 4 ffn-up gemm, 5 ffn-down gemm, 6 pool. */
+#define RPX_N_KERNEL_CLASSES 7
+int rpx_encoder_set_profiling(rpx_encoder* enc, int32_t enable);
+/* Synchronises the recorded events; adds elapsed ms / launch counts since the
+ * last read into ms[RPX_N_KERNEL_CLASSES], launches[RPX_N_KERNEL_CLASSES]. */
+int rpx_encoder_read_profile(rpx_encoder* enc, float* h_ms, int64_t* h_launches);
+
+/* --------------------------------------------------------------- similarity + top-k
+ * Replaces the matmul + argsort half of `Corpus.get_nearest_premises`
+ * (common.py:307-308) and the first-k walk at :316-322:
+ *     S = Q E^T ; per query the k best rows of E, best first.
+ * Ordering contract (deterministic refinement of the reference's unspecified
+ * argsort tie order): score descending, then index ascending, where `score` is
+ * the canonical fp64 dot product of the bf16 operands (oracle/rpx_oracle.c:
+ * rpx_oracle_dot64).  out_scores are that value rounded to fp32.
+ *   d_Q [nq, d] bf16, d_E [n, d] bf16 (the dtype the reference's GPU path holds
+ *   the index in, retrieval/model.py:363-366); d % 64 == 0; 1 <= k <= 256.
+ *   d_access_mask  optional bitmask, row q = mask_stride_words uint32 words, bit
+ *                  (i & 31) of word i >> 5 set <=> premise i is accessible to query q
+ *                  (the `p in accessible_premises` test, common.py:313-318).
+ *   d_out_count    optional [nq]: number of valid results (< k when fewer than k
+ *                  candidates exist; the tail is idx = -1, score = -inf).
+ *   idx_offset     added to every output index (row offset of this shard).
+ */
+size_t rpx_sim_topk_workspace_bytes(int32_t nq, int32_t k);
+int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_t d, int32_t k,
+                 const uint32_t* d_access_mask, int64_t mask_stride_words, float* d_out_scores,
+                 double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count,
+                 int64_t idx_offset, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* k-way merge of per-shard results after the all-gather:
+ * inputs [n_parts, nq, k] (fp64 scores, int64 global indices, idx < 0 = empty),
+ * outputs the global top-k per query under the same ordering contract. */
+int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_parts, int32_t nq,
+                   int32_t k, float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx,
+                   int32_t* d_out_count, void* stream);
+
+/* ------------------------------------------------------------------- test utilities
+ * Plain tcgen05 GEMM used by the parity tests of the contraction core:
+ * C[M, N] (fp32, ldc = N) = A[M, K] * B[N, K]^T, bf16 inputs; K % 64 == 0, N % 32 == 0. */
+int rpx_gemm_bf16_f32(const void* d_A, const void* d_B, float* d_C, int32_t M, int32_t N,
+                      int32_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPX_H_ */

@@ -1,0 +1,95 @@
+// rpx_common.cu — error plumbing, device info, TMA tensor-map encoding.
+#include "rpx_common.cuh"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+#include <mutex>
+
+namespace rpx {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// cuTensorMapEncodeTiled is a driver entry point.  Resolving it through the
+// runtime keeps libcuda.so.1 out of the link line, so the library still loads
+// (and exports its symbols) on a build box with no driver installed.
+static PFN_cuTensorMapEncodeTiled_v12000 resolve_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault,
+                                         &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                      uint64_t ld_elems, uint32_t box_rows) {
+  auto encode = resolve_encode();
+  RPX_REQUIRE(encode != nullptr, RPX_ERR_CUDA, "cuTensorMapEncodeTiled not available from driver");
+  RPX_REQUIRE((reinterpret_cast<uintptr_t>(gptr) & 15) == 0, RPX_ERR_INVALID,
+              "TMA operand base must be 16-byte aligned");
+  RPX_REQUIRE((ld_elems * 2) % 16 == 0, RPX_ERR_INVALID, "TMA row pitch must be a multiple of 16 bytes");
+  RPX_REQUIRE(box_rows >= 1 && box_rows <= 256, RPX_ERR_INVALID, "TMA box rows out of range");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RPX_REQUIRE(r == CUDA_SUCCESS, RPX_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+  return RPX_OK;
+}
+
+int get_device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  int dev = -1;
+  RPX_CUDA_OK(cudaGetDevice(&dev));
+  RPX_REQUIRE(dev >= 0 && dev < 64, RPX_ERR_CUDA, "unexpected device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    RPX_CUDA_OK(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RPX_CUDA_OK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    RPX_CUDA_OK(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    int optin = 0;
+    RPX_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    d.smem_optin = (size_t)optin;
+    cache[dev] = d;
+  }
+  *out = cache[dev];
+  RPX_REQUIRE(out->cc_major == 10, RPX_ERR_UNSUPPORTED,
+              "device %d is sm_%d%d; this engine is sm_100a (B200) only", dev, out->cc_major,
+              out->cc_minor);
+  return RPX_OK;
+}
+
+}  // namespace rpx
+
+extern "C" {
+
+const char* rpx_last_error(void) { return rpx::get_error(); }
+int rpx_version(void) { return RPX_VERSION; }
+int rpx_device_check(void) {
+  rpx::DeviceInfo d;
+  return rpx::get_device_info(&d);
+}
+
+}  // extern "C"

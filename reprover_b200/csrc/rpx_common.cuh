@@ -1,0 +1,63 @@
+// rpx_common.cuh — host-side plumbing shared by every translation unit:
+// error codes + thread-local last-error string, CUDA call checking, the TMA
+// tensor-map encoder (resolved from the driver at run time so the library loads
+// on a machine without libcuda.so.1), device property cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rpx.h"
+
+namespace rpx {
+
+// Thread-local message behind rpx_last_error().
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define RPX_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::rpx::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                       cudaGetErrorString(_e));                                            \
+      return RPX_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define RPX_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::rpx::set_error(__VA_ARGS__);   \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+#define RPX_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != RPX_OK) return _s; \
+  } while (0)
+
+// Encodes a 2-D row-major bf16 tensor [rows, cols] (cols contiguous, row pitch
+// `ld_elems`) as a TMA map with a {box_cols=64, box_rows} box and 128-byte swizzle.
+// Out-of-bounds box elements are zero-filled.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                      uint64_t ld_elems, uint32_t box_rows);
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+};
+// Properties of the current device (cached per device ordinal).  Fails unless sm_100.
+int get_device_info(DeviceInfo* out);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace rpx

@@ -1,0 +1,403 @@
+// rpx_gemm.cuh — the tcgen05 / TMA / TMEM contraction core shared by the encoder
+// GEMMs and the similarity kernel.
+//
+//   D[M, N] (fp32, in TMEM) = A[M, K] * B[N, K]^T        A, B bf16, K contiguous
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer   — cp.async.bulk.tensor A/B tiles into a STAGES-deep
+//                 128B-swizzled shared-memory ring, completion on `full[]` mbarriers
+//   warp 1      : MMA issuer     — one elected thread issues tcgen05.mma (M=128,
+//                 N<=256, K=16) x4 per stage; tcgen05.commit releases the stage
+//                 (`empty[]`) and, after the last k-block, publishes the accumulator
+//                 (`tfull[]`).  Also owns TMEM alloc/dealloc.
+//   warps 2..5  : epilogue       — tcgen05.ld the accumulator (one row per thread)
+//                 and run the fused epilogue functor; `tempty[]` hands the TMEM
+//                 stage back.  Two accumulator stages (2 x BLOCK_N columns) let the
+//                 epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Tiles are visited in n-fastest order so that concurrently resident CTAs share
+// the same A row-block through L2 (the B operand — weights, or the query block
+// for the similarity kernel — is small and L2-resident).
+//
+// The reference has no counterpart: it calls torch `@` / nn.Linear (cuBLAS) —
+// SURVEY.md §2.1 K3/K8/K9/K11.
+#pragma once
+#include "rpx_ptx.cuh"
+
+namespace rpx {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarp0 = 2;  // first epilogue warp
+
+template <int BLOCK_N, int STAGES>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+  static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512,
+                "TMEM allocation must be a power of two in [32, 512]");
+  // ring + 1 KB alignment slack + barriers/tmem pointer
+  static constexpr int kBarBytes = 256;
+  static constexpr size_t smem_bytes(size_t epi_extra) {
+    return (size_t)STAGES * kStageBytes + 1024 + kBarBytes + epi_extra;
+  }
+};
+
+// What an epilogue functor sees for one output tile.
+struct TileCtx {
+  uint32_t tmem;   // TMEM address of this thread's row, column 0 of the accumulator stage
+  int m0, n0;      // tile origin in the output
+  int n_cols;      // valid columns in this tile (multiple of 32)
+  int row;         // this thread's row inside the tile, 0..127
+  int m_blk, n_blk;
+  int M, N;
+};
+
+// Epi must provide:
+//   struct Params;                       (trivially copyable kernel argument)
+//   static constexpr size_t kSmemBytes;  (extra dynamic shared memory, may be 0)
+//   __device__ Epi(const Params&, uint8_t* smem_extra, int epi_tid /*0..127*/);
+//   __device__ void tile(const TileCtx&);     (all 128 epilogue threads, warp-converged)
+//   __device__ void finish();
+template <int BLOCK_N, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, int tiles_m, int tiles_n, typename Epi::Params ep) {
+  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tile bases.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* smem_extra = smem + STAGES * Cfg::kStageBytes + Cfg::kBarBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = K / kBlockK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull[s], 1);
+        mbar_init(&tempty[s], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % tiles_n;
+        const int m_blk = tile / tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK,
+                      m_blk * kBlockM);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
+                      n_blk * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % tiles_n;
+        int n_this = N - n_blk * BLOCK_N;
+        if (n_this > BLOCK_N) n_this = BLOCK_N;
+        n_this = (n_this + 15) & ~15;
+        const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)n_this);
+        mbar_wait(&tempty[as], aphase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t b_desc = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int epi_tid = threadIdx.x - kEpiWarp0 * 32;         // 0..127
+    const int lane_grp = warp & 3;                            // TMEM lane group this warp may read
+    const int row = lane_grp * 32 + (threadIdx.x & 31);       // row of the tile this thread owns
+    Epi epi(ep, smem_extra, epi_tid);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      TileCtx t;
+      t.n_blk = tile % tiles_n;
+      t.m_blk = tile / tiles_n;
+      t.m0 = t.m_blk * kBlockM;
+      t.n0 = t.n_blk * BLOCK_N;
+      int n_this = N - t.n0;
+      if (n_this > BLOCK_N) n_this = BLOCK_N;
+      t.n_cols = n_this;
+      t.row = row;
+      t.M = M;
+      t.N = N;
+      t.tmem = tmem_base + as * BLOCK_N + ((uint32_t)(lane_grp * 32) << 16);
+      mbar_wait(&tfull[as], aphase, 4);
+      tc_fence_after();
+      epi.tile(t);
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    epi.finish();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ============================================================================ epilogues
+
+// Row scale shared by the epilogues that consume an RMSNorm'd operand: the
+// RMSNorm weight is folded into the GEMM's B operand at load time, so all that
+// is left is rs[m] = rsqrt(mean_k(x[m,k]^2) + eps), applied to the fp32 accumulator.
+// sumsq is delivered as `n_parts` partial sums per row (written by the producing
+// epilogue, one per output n-block), summed here in a fixed order -> deterministic.
+struct RowScale {
+  const float* ss_parts;  // [n_parts][M] or nullptr (scale 1)
+  int n_parts;
+  int part_stride;        // elements between parts (>= M)
+  float inv_dim;          // 1 / d_model
+  float eps;
+  __device__ float get(int m) const {
+    if (ss_parts == nullptr) return 1.0f;
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += ss_parts[(size_t)p * part_stride + m];
+    return rsqrtf(s * inv_dim + eps);
+  }
+};
+
+// C[m, n] = acc (fp32).  Generic; used by tests.
+struct EpiStoreF32 {
+  struct Params {
+    float* C;
+    int ldc;
+  };
+  static constexpr size_t kSmemBytes = 0;
+  Params p;
+  __device__ EpiStoreF32(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ void tile(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    const bool ok = m < t.M;
+    for (int c = 0; c < t.n_cols; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t.tmem + c, v);
+      tmem_ld_wait();
+      if (ok) {
+        float4* dst = reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + t.n0 + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+  __device__ void finish() {}
+};
+
+// C[m, n] = bf16(acc * rs[m]).  QKV projection (RMSNorm folded: prologue of K3).
+struct EpiStoreBF16 {
+  struct Params {
+    __nv_bfloat16* C;
+    int ldc;
+    RowScale rs;
+  };
+  static constexpr size_t kSmemBytes = 0;
+  Params p;
+  __device__ EpiStoreBF16(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ void tile(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    const bool ok = m < t.M;
+    const float rs = ok ? p.rs.get(m) : 0.f;
+    for (int c = 0; c < t.n_cols; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t.tmem + c, v);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.C + (size_t)m * p.ldc + t.n0 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * rs, __uint_as_float(v[8 * i + 1]) * rs);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * rs, __uint_as_float(v[8 * i + 3]) * rs);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * rs, __uint_as_float(v[8 * i + 5]) * rs);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * rs, __uint_as_float(v[8 * i + 7]) * rs);
+          dst[i] = o;
+        }
+      }
+    }
+  }
+  __device__ void finish() {}
+};
+
+// Residual update (attention output projection K8 and FFN down projection K9):
+//   h32[m, n] += acc;  h16[m, n] = bf16(h32[m, n]);  ss_out[n_blk][m] = sum_n h32[m, n]^2
+// The fp32 copy is the residual stream; the bf16 copy is the next GEMM's A operand;
+// ss_out feeds the next RMSNorm (see RowScale).
+struct EpiResidual {
+  struct Params {
+    float* h32;
+    __nv_bfloat16* h16;
+    int ld;
+    float* ss_out;  // [tiles_n][ss_stride]
+    int ss_stride;
+  };
+  static constexpr size_t kSmemBytes = 0;
+  Params p;
+  __device__ EpiResidual(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ void tile(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    const bool ok = m < t.M;
+    float ss = 0.f;
+    for (int c = 0; c < t.n_cols; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t.tmem + c, v);
+      tmem_ld_wait();
+      if (ok) {
+        float4* hp = reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + t.n0 + c);
+        uint4* bp = reinterpret_cast<uint4*>(p.h16 + (size_t)m * p.ld + t.n0 + c);
+        float4 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = hp[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          h[i].x += __uint_as_float(v[4 * i + 0]);
+          h[i].y += __uint_as_float(v[4 * i + 1]);
+          h[i].z += __uint_as_float(v[4 * i + 2]);
+          h[i].w += __uint_as_float(v[4 * i + 3]);
+          ss += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
+          hp[i] = h[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(h[2 * i].x, h[2 * i].y);
+          o.y = pack_bf16x2(h[2 * i].z, h[2 * i].w);
+          o.z = pack_bf16x2(h[2 * i + 1].x, h[2 * i + 1].y);
+          o.w = pack_bf16x2(h[2 * i + 1].z, h[2 * i + 1].w);
+          bp[i] = o;
+        }
+      }
+    }
+    if (ok) p.ss_out[(size_t)t.n_blk * p.ss_stride + m] = ss;
+  }
+  __device__ void finish() {}
+};
+
+// gelu_new (tanh form) — HF activations.py NewGELUActivation, used by T5 "gated-gelu".
+__device__ __forceinline__ float gelu_new(float x) {
+  const float k0 = 0.7978845608028654f;  // sqrt(2/pi)
+  const float k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+
+// Gated-GELU FFN up projection (K9): the B operand interleaves wi_0 / wi_1 in
+// 128-row blocks, so accumulator columns [0,128) are the gate and [128,256) the
+// linear branch of the same 128 hidden units.
+//   out[m, n_blk*128 + j] = bf16( gelu_new(acc[j]*rs) * (acc[128+j]*rs) )
+struct EpiGeGLU {
+  struct Params {
+    __nv_bfloat16* out;  // [M, N/2]
+    int ldo;
+    RowScale rs;
+  };
+  static constexpr size_t kSmemBytes = 0;
+  Params p;
+  __device__ EpiGeGLU(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ void tile(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    const bool ok = m < t.M;
+    const float rs = ok ? p.rs.get(m) : 0.f;
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t g[32], u[32];
+      tmem_ld_32x32(t.tmem + c, g);
+      tmem_ld_32x32(t.tmem + 128 + c, u);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + t.n_blk * 128 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            r[j] = gelu_new(__uint_as_float(g[8 * i + j]) * rs) * (__uint_as_float(u[8 * i + j]) * rs);
+          uint4 o;
+          o.x = pack_bf16x2(r[0], r[1]);
+          o.y = pack_bf16x2(r[2], r[3]);
+          o.z = pack_bf16x2(r[4], r[5]);
+          o.w = pack_bf16x2(r[6], r[7]);
+          dst[i] = o;
+        }
+      }
+    }
+  }
+  __device__ void finish() {}
+};
+
+}  // namespace rpx

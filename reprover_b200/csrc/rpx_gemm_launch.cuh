@@ -1,0 +1,43 @@
+// rpx_gemm_launch.cuh — host-side launcher for gemm_tc_kernel.
+#pragma once
+#include "rpx_common.cuh"
+#include "rpx_gemm.cuh"
+
+namespace rpx {
+
+constexpr int kGemmStages = 4;
+
+// A: [M, K] bf16 (row pitch lda), B: [N, K] bf16 (row pitch ldb).  K % 64 == 0, N % 32 == 0.
+// `grid_limit` caps the persistent grid (0 = one CTA per SM).
+template <int BLOCK_N, class Epi>
+int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                const typename Epi::Params& ep, cudaStream_t stream, int grid_limit = 0) {
+  using Cfg = GemmCfg<BLOCK_N, kGemmStages>;
+  RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
+  RPX_REQUIRE(N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  CUtensorMap tmA, tmB;
+  RPX_TRY(make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockM));
+  RPX_TRY(make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BLOCK_N));
+  const int tiles_m = ceil_div(M, kBlockM);
+  const int tiles_n = ceil_div(N, BLOCK_N);
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "gemm: needs %zu B smem, device allows %zu",
+              smem, dev.smem_optin);
+  auto kern = gemm_tc_kernel<BLOCK_N, kGemmStages, Epi>;
+  static thread_local int configured_dev = -1;  // per-instantiation, per-thread
+  if (configured_dev != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev.device;
+  }
+  int grid = tiles_m * tiles_n;
+  int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
+  if (grid > cap) grid = cap;
+  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, ep);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+}  // namespace rpx
