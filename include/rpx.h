@@ -114,6 +114,7 @@ size_t rpx_encoder_workspace_bytes(const rpx_encoder* enc, int64_t max_tokens, i
  *   h_offsets   n_seqs + 1 byte offsets into d_bytes (HOST; the host needs the
  *               lengths to size the launch)
  *   d_out       [n_seqs, d_model] unit-norm rows, RPX_DTYPE_BF16 or RPX_DTYPE_F32
+ * If h_offsets is page-locked memory it must stay valid until `stream` reaches this call.
  * Strings must not contain ByT5 special-token literals ("</s>", "<pad>", "<unk>",
  * "<extra_id_N>"); callers route those through rpx_encode_ids (the Python shim does). */
 int rpx_encode_bytes(rpx_encoder* enc, const uint8_t* d_bytes, const int64_t* h_offsets,
@@ -128,6 +129,11 @@ int rpx_encode_bytes(rpx_encoder* enc, const uint8_t* d_bytes, const int64_t* h_
 int rpx_encode_ids(rpx_encoder* enc, const int64_t* d_input_ids, const int64_t* d_attention_mask,
                    int32_t batch, int32_t seq_len, void* d_out, int32_t out_dtype,
                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* T5 bidirectional relative-position bucket of `relative_position` = key - query
+ * (HF modeling_t5.py:189-234).  Pure host function (no GPU needed); exported so the
+ * CPU test-suite can pin the table the attention kernel uses against the HF code. */
+int32_t rpx_t5_relative_bucket(int32_t relative_position, int32_t num_buckets, int32_t max_distance);
 
 /* Debug / parity hook: when non-NULL, every encode call also writes the fp32
  * residual stream after the embedding and after each block to

@@ -1,0 +1,226 @@
+// rpx_elementwise.cu — the HBM-bound byte / row kernels around the GEMMs:
+// ByT5 tokenisation (K1 prologue), embedding gather (K1), final RMSNorm + masked
+// mean-pool + L2 normalise (K2 + K10), attention-mask validation, weight packing.
+// All are coalesced, vectorised (16-byte) row streams; none is reshaped into a GEMM.
+#include "rpx_common.cuh"
+#include "rpx_kernels.cuh"
+#include "rpx_ptx.cuh"
+
+namespace rpx {
+
+namespace {
+
+// Largest s with cu[s] <= t  (cu is non-decreasing, cu[0] = 0, cu[n] > t).
+__device__ __forceinline__ int find_seq(const int32_t* __restrict__ cu, int n, int t) {
+  int lo = 0, hi = n;  // invariant: cu[lo] <= t < cu[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cu[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// HF ByT5Tokenizer (tokenization_byt5.py:195-208): id = byte + 3; EOS (1) appended;
+// truncation keeps max_len - 1 bytes + EOS.  cu_tokens already encodes the truncation.
+__global__ void tokenize_bytes_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ cu_bytes,
+                                      const int32_t* __restrict__ cu_tokens, int32_t* __restrict__ ids,
+                                      int n_seqs, int n_tokens) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tokens) return;
+  const int s = find_seq(cu_tokens, n_seqs, t);
+  const int p = t - cu_tokens[s];
+  const int last = cu_tokens[s + 1] - cu_tokens[s] - 1;
+  ids[t] = (p == last) ? 1 : (int32_t)bytes[cu_bytes[s] + p] + 3;
+}
+
+__global__ void pack_ids_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ cu_tokens,
+                                int32_t* __restrict__ packed, int batch, int seq_len, int n_tokens,
+                                int vocab, int32_t* __restrict__ bad_flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tokens) return;
+  const int s = find_seq(cu_tokens, batch, t);
+  const int p = t - cu_tokens[s];
+  const int64_t id = ids[(int64_t)s * seq_len + p];
+  if (id < 0 || id >= vocab) {
+    atomicOr(bad_flag, 2);
+    packed[t] = 0;
+  } else {
+    packed[t] = (int32_t)id;
+  }
+}
+
+__global__ void mask_lengths_kernel(const int64_t* __restrict__ mask, int32_t* __restrict__ lens,
+                                    int32_t* __restrict__ bad_flag, int batch, int seq_len) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= batch) return;
+  int cnt = 0, last = -1, bad = 0;
+  for (int j = lane; j < seq_len; j += 32) {
+    const int64_t m = mask[(int64_t)row * seq_len + j];
+    if (m != 0 && m != 1) bad = 1;
+    if (m != 0) {
+      ++cnt;
+      last = j;
+    }
+  }
+  for (int off = 16; off; off >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, off));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if (lane == 0) {
+    lens[row] = cnt;
+    if (bad || cnt == 0 || cnt != last + 1) atomicOr(bad_flag, 1);
+  }
+}
+
+// One warp per token.
+__global__ void embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ table,
+                             float* __restrict__ h32, __nv_bfloat16* __restrict__ h16, float* __restrict__ ss,
+                             int ss_stride, int n_parts, int n_tokens, int d_model) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= n_tokens) return;
+  const float4* src = reinterpret_cast<const float4*>(table + (int64_t)ids[t] * d_model);
+  float4* d32 = reinterpret_cast<float4*>(h32 + (int64_t)t * d_model);
+  uint2* d16 = reinterpret_cast<uint2*>(h16 + (int64_t)t * d_model);
+  float acc = 0.f;
+  for (int i = lane; i < d_model / 4; i += 32) {
+    const float4 v = src[i];
+    d32[i] = v;
+    d16[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    ss[t] = acc;
+    for (int p = 1; p < n_parts; ++p) ss[(int64_t)p * ss_stride + t] = 0.f;
+  }
+}
+
+// One CTA per sequence; thread i owns dims [4i, 4i+4).
+__global__ void pool_normalize_kernel(const float* __restrict__ h32, const float* __restrict__ ss, int ss_stride,
+                                      int n_parts, const float* __restrict__ ln_w,
+                                      const int32_t* __restrict__ cu_tokens, void* __restrict__ out,
+                                      int out_dtype, int d_model, float eps) {
+  const int s = blockIdx.x;
+  const int t0 = cu_tokens[s], t1 = cu_tokens[s + 1];
+  const int i = threadIdx.x;
+  const bool active = i < d_model / 4;
+  const float inv_d = 1.0f / (float)d_model;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = t0; t < t1; ++t) {
+    float sum = 0.f;
+    for (int p = 0; p < n_parts; ++p) sum += ss[(int64_t)p * ss_stride + t];
+    const float rs = rsqrtf(sum * inv_d + eps);
+    if (active) {
+      const float4 v = reinterpret_cast<const float4*>(h32 + (int64_t)t * d_model)[i];
+      acc.x += v.x * rs;
+      acc.y += v.y * rs;
+      acc.z += v.z * rs;
+      acc.w += v.w * rs;
+    }
+  }
+  const float inv_len = 1.0f / (float)(t1 - t0);
+  float sq = 0.f;
+  if (active) {
+    const float4 w = reinterpret_cast<const float4*>(ln_w)[i];
+    acc.x *= w.x * inv_len;
+    acc.y *= w.y * inv_len;
+    acc.z *= w.z * inv_len;
+    acc.w *= w.w * inv_len;
+    sq = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  __shared__ float red[32];
+  for (int off = 16; off; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  // F.normalize: x / max(||x||_2, 1e-12)
+  const float inv_norm = 1.0f / fmaxf(sqrtf(red[0]), 1e-12f);
+  if (active) {
+    acc.x *= inv_norm;
+    acc.y *= inv_norm;
+    acc.z *= inv_norm;
+    acc.w *= inv_norm;
+    if (out_dtype == RPX_DTYPE_F32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (int64_t)s * d_model)[i] = acc;
+    } else {
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (int64_t)s * d_model)[i] =
+          make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
+  }
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                   __nv_bfloat16* __restrict__ dst, int n_rows, int n_cols, int dst_row0,
+                                   int blk, int blk_stride) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_rows * n_cols) return;
+  const int n = (int)(idx / n_cols), k = (int)(idx % n_cols);
+  const float v = src[idx] * (scale ? scale[k] : 1.0f);
+  const int64_t drow = dst_row0 + (int64_t)(n / blk) * blk_stride + (n % blk);
+  dst[drow * n_cols + k] = __float2bfloat16_rn(v);
+}
+
+}  // namespace
+
+int launch_tokenize_bytes(const uint8_t* bytes, const int64_t* cu_bytes, const int32_t* cu_tokens,
+                          int32_t* ids, int n_seqs, int n_tokens, cudaStream_t stream) {
+  tokenize_bytes_kernel<<<ceil_div(n_tokens, 256), 256, 0, stream>>>(bytes, cu_bytes, cu_tokens, ids, n_seqs,
+                                                                     n_tokens);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+int launch_pack_ids(const int64_t* ids, const int32_t* cu_tokens, int32_t* packed, int batch, int seq_len,
+                    int n_tokens, int vocab, int32_t* bad_flag, cudaStream_t stream) {
+  pack_ids_kernel<<<ceil_div(n_tokens, 256), 256, 0, stream>>>(ids, cu_tokens, packed, batch, seq_len, n_tokens,
+                                                               vocab, bad_flag);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+int launch_mask_lengths(const int64_t* mask, int32_t* lens, int32_t* bad_flag, int batch, int seq_len,
+                        cudaStream_t stream) {
+  mask_lengths_kernel<<<ceil_div(batch, 8), 256, 0, stream>>>(mask, lens, bad_flag, batch, seq_len);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+int launch_embed(const int32_t* ids, const float* table, float* h32, __nv_bfloat16* h16, float* ss,
+                 int ss_stride, int n_parts, int n_tokens, int d_model, cudaStream_t stream) {
+  RPX_REQUIRE(d_model % 4 == 0, RPX_ERR_UNSUPPORTED, "embed: d_model must be a multiple of 4");
+  embed_kernel<<<ceil_div(n_tokens, 8), 256, 0, stream>>>(ids, table, h32, h16, ss, ss_stride, n_parts, n_tokens,
+                                                          d_model);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+int launch_pool_normalize(const float* h32, const float* ss, int ss_stride, int n_parts, const float* ln_w,
+                          const int32_t* cu_tokens, void* out, int out_dtype, int n_seqs, int d_model,
+                          float eps, cudaStream_t stream) {
+  const int threads = (int)align_up((size_t)d_model / 4, 32);
+  RPX_REQUIRE(d_model % 4 == 0 && threads <= 1024, RPX_ERR_UNSUPPORTED, "pool: unsupported d_model=%d", d_model);
+  RPX_REQUIRE(out_dtype == RPX_DTYPE_BF16 || out_dtype == RPX_DTYPE_F32, RPX_ERR_INVALID, "pool: bad out dtype");
+  pool_normalize_kernel<<<n_seqs, threads, 0, stream>>>(h32, ss, ss_stride, n_parts, ln_w, cu_tokens, out,
+                                                        out_dtype, d_model, eps);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+int launch_pack_weight(const float* src, const float* scale, __nv_bfloat16* dst, int n_rows, int n_cols,
+                       int dst_row0, int blk, int blk_stride, cudaStream_t stream) {
+  const int64_t n = (int64_t)n_rows * n_cols;
+  pack_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(src, scale, dst, n_rows, n_cols, dst_row0,
+                                                                        blk, blk_stride);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+}  // namespace rpx

@@ -1,0 +1,126 @@
+"""Parity of the CUDA encoder path (rpx_encode_bytes / rpx_encode_ids through the C ABI)
+against the HF-based CPU oracle on the same synthetic checkpoint and inputs."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from reprover_b200 import _native, synth
+from reprover_b200.engine import T5EncoderEngine
+from tests.helpers import EMB_MAX_ABS, EMB_MIN_COS, compare_embeddings, oracle_embeddings, ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _hidden_report(engine, cfg, sd, data, offsets, max_len, out_dir, tag):
+    """Layer-by-layer relative error of the residual stream (diagnostic artefact)."""
+    texts = [s.decode() for s in synth.split_strings(data, offsets)]
+    enc = ref.build_hf_encoder(cfg, sd)
+    tok = ref.tokenize(ref.build_hf_tokenizer(), texts, max_len)
+    with torch.no_grad():
+        hs = enc(input_ids=tok.input_ids, attention_mask=tok.attention_mask, output_hidden_states=True).hidden_states
+    lens = tok.attention_mask.sum(1).tolist()
+    T = int(sum(lens))
+    dump = engine.set_debug_hidden(T)
+    engine.encode_bytes(data, offsets, max_len)
+    torch.cuda.synchronize()
+    dump = dump.cpu()
+    engine.set_debug_hidden(None)
+    rows = []
+    for l in range(cfg["num_layers"]):
+        want = torch.cat([hs[l][b, :lens[b]] for b in range(len(lens))], 0)
+        err = (dump[l] - want).abs().max().item()
+        rel = err / want.abs().max().item()
+        rows.append({"layer_in": l, "max_abs": err, "rel_to_max": rel})
+    (out_dir / f"encoder_hidden_{tag}.json").write_text(json.dumps(rows, indent=1))
+    return rows
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = synth.tiny_config(num_layers=2)
+    return cfg, synth.random_t5_state_dict(cfg, seed=11)
+
+
+def test_tiny_encoder_matches_oracle(rpx_lib, cuda_device, out_dir, tiny):
+    cfg, sd = tiny
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    # ragged lengths incl. 1-byte strings, tile boundaries (63/64/65, 127/128) and > 2 key tiles
+    lens = [1, 5, 62, 63, 64, 127, 128, 200, 300, 511]
+    rng = np.random.default_rng(5)
+    strs = [bytes(rng.choice(synth._ALPHABET, size=n).tolist()) for n in lens]
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in strs])]).astype(np.int64)
+    data = np.frombuffer(b"".join(strs), dtype=np.uint8)
+    got = eng.encode_bytes(data, offsets, 512, out_dtype=torch.float32)
+    want = oracle_embeddings(cfg, sd, data, offsets, 512)
+    max_abs, min_cos = compare_embeddings(got, want)
+    rows = _hidden_report(eng, cfg, sd, data, offsets, 512, out_dir, "tiny")
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos, rows)
+    norms = got.float().norm(dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=1e-4)
+
+
+def test_truncation_and_bf16_output(rpx_lib, cuda_device, tiny):
+    cfg, sd = tiny
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    data, offsets = synth.synth_premises(12, seed=3, min_len=100, max_len=400)
+    # max_seq_len 128 truncates most strings to 127 bytes + EOS (HF: truncation includes the EOS)
+    got = eng.encode_bytes(data, offsets, 128, out_dtype=torch.bfloat16)
+    want = oracle_embeddings(cfg, sd, data, offsets, 128)
+    max_abs, min_cos = compare_embeddings(got, want)
+    assert max_abs <= EMB_MAX_ABS + 2e-3 and min_cos >= EMB_MIN_COS, (max_abs, min_cos)  # + bf16 output rounding
+
+
+def test_encode_ids_signature_parity(rpx_lib, cuda_device, tiny):
+    """`_encode(input_ids, attention_mask)` on padded int64 tensors == the packed-bytes path."""
+    cfg, sd = tiny
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    data, offsets = synth.synth_premises(7, seed=9, min_len=3, max_len=90)
+    texts = [s.decode() for s in synth.split_strings(data, offsets)]
+    tok = ref.tokenize(ref.build_hf_tokenizer(), texts, 64)
+    a = eng.encode_ids(tok.input_ids.to(cuda_device), tok.attention_mask.to(cuda_device), out_dtype=torch.float32)
+    b = eng.encode_bytes(data, offsets, 64, out_dtype=torch.float32)
+    assert torch.equal(a, b)
+    want = ref.encode(ref.build_hf_encoder(cfg, sd), tok.input_ids, tok.attention_mask)
+    max_abs, min_cos = compare_embeddings(a, want)
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
+
+
+def test_encode_ids_rejects_non_prefix_mask(rpx_lib, cuda_device, tiny):
+    cfg, sd = tiny
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    ids = torch.randint(3, 259, (2, 16), device=cuda_device)
+    mask = torch.ones(2, 16, dtype=torch.int64, device=cuda_device)
+    mask[1, 5] = 0  # hole
+    with pytest.raises(_native.RpxError) as ei:
+        eng.encode_ids(ids, mask)
+    assert ei.value.code == _native.RPX_ERR_MASK
+    mask = torch.ones(2, 16, dtype=torch.int64, device=cuda_device)
+    mask[0, :] = 0  # empty row (the reference would divide by zero)
+    with pytest.raises(_native.RpxError):
+        eng.encode_ids(ids, mask)
+    bad = ids.clone()
+    bad[0, 0] = 999
+    with pytest.raises(_native.RpxError):
+        eng.encode_ids(bad, torch.ones(2, 16, dtype=torch.int64, device=cuda_device))
+
+
+def test_byt5_small_cfg1(rpx_lib, cuda_device, out_dir):
+    """BASELINE config 1: full ByT5-small geometry, 8 premises + 1 state, cosine top-3."""
+    cfg = dict(synth.BYT5_SMALL)
+    sd = synth.random_t5_state_dict(cfg, seed=synth.SEED)
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    pd, po = synth.synth_premises(8, seed=synth.SEED)
+    sdt, so = synth.synth_states(1, seed=synth.SEED + 1)
+    data = np.concatenate([pd, sdt])
+    offsets = np.concatenate([po, po[-1] + so[1:]])
+    got = eng.encode_bytes(data, offsets, 512, out_dtype=torch.float32)
+    want = oracle_embeddings(cfg, sd, data, offsets, 512)
+    max_abs, min_cos = compare_embeddings(got, want)
+    rows = _hidden_report(eng, cfg, sd, data, offsets, 512, out_dir, "byt5small")
+    (out_dir / "encoder_cfg1.json").write_text(json.dumps({"max_abs": max_abs, "min_cos": min_cos}))
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos, rows)
+    sims_got = (got[8:] @ got[:8].t()).cpu()
+    sims_want = want[8:] @ want[:8].t()
+    assert torch.allclose(sims_got, sims_want, atol=4e-3)
