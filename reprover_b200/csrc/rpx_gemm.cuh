@@ -16,8 +16,10 @@
 //                 epilogue of tile i overlap the mainloop of tile i+1.
 //
 // Tiles are visited in n-fastest order so that concurrently resident CTAs share
-// the same A row-block through L2 (the B operand — weights, or the query block
-// for the similarity kernel — is small and L2-resident).
+// the same A row-block through L2 (the B operand — the weights — is small and
+// L2-resident).  The similarity kernel uses M_FASTEST instead: A is the (small)
+// query block, B the streamed corpus, and a grid that is a multiple of tiles_m
+// pins every CTA to one query block for its whole life.
 //
 // The reference has no counterpart: it calls torch `@` / nn.Linear (cuBLAS) —
 // SURVEY.md §2.1 K3/K8/K9/K11.
@@ -60,10 +62,10 @@ struct TileCtx {
 // Epi must provide:
 //   struct Params;                       (trivially copyable kernel argument)
 //   static constexpr size_t kSmemBytes;  (extra dynamic shared memory, may be 0)
-//   __device__ Epi(const Params&, uint8_t* smem_extra, int epi_tid /*0..127*/);
+//   __device__ Epi(const Params&, uint8_t* smem_extra, int row /*tile row this thread owns, 0..127*/);
 //   __device__ void tile(const TileCtx&);     (all 128 epilogue threads, warp-converged)
 //   __device__ void finish();
-template <int BLOCK_N, int STAGES, class Epi>
+template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int tiles_m, int tiles_n, typename Epi::Params ep) {
@@ -116,8 +118,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % tiles_n;
-        const int m_blk = tile / tiles_n;
+        const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
+        const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -140,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % tiles_n;
+        const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         int n_this = N - n_blk * BLOCK_N;
         if (n_this > BLOCK_N) n_this = BLOCK_N;
         n_this = (n_this + 15) & ~15;
@@ -171,16 +173,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int epi_tid = threadIdx.x - kEpiWarp0 * 32;         // 0..127
     const int lane_grp = warp & 3;                            // TMEM lane group this warp may read
     const int row = lane_grp * 32 + (threadIdx.x & 31);       // row of the tile this thread owns
-    Epi epi(ep, smem_extra, epi_tid);
+    Epi epi(ep, smem_extra, row);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       TileCtx t;
-      t.n_blk = tile % tiles_n;
-      t.m_blk = tile / tiles_n;
+      t.n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
+      t.m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
       t.m0 = t.m_blk * kBlockM;
       t.n0 = t.n_blk * BLOCK_N;
       int n_this = N - t.n0;

@@ -9,13 +9,15 @@ constexpr int kGemmStages = 4;
 
 // A: [M, K] bf16 (row pitch lda), B: [N, K] bf16 (row pitch ldb).  K % 64 == 0, N % 32 == 0.
 // `grid_limit` caps the persistent grid (0 = one CTA per SM).
-template <int BLOCK_N, class Epi>
+// M_FASTEST kernels take the grid size verbatim from `grid_limit` (the caller sizes it as a
+// multiple of tiles_m) and accept any N (the epilogue masks the ragged tail).
+template <int BLOCK_N, class Epi, bool M_FASTEST = false>
 int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 const typename Epi::Params& ep, cudaStream_t stream, int grid_limit = 0) {
   using Cfg = GemmCfg<BLOCK_N, kGemmStages>;
   RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
-  RPX_REQUIRE(N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
+  RPX_REQUIRE(M_FASTEST || N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   CUtensorMap tmA, tmB;
@@ -26,7 +28,7 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "gemm: needs %zu B smem, device allows %zu",
               smem, dev.smem_optin);
-  auto kern = gemm_tc_kernel<BLOCK_N, kGemmStages, Epi>;
+  auto kern = gemm_tc_kernel<BLOCK_N, kGemmStages, Epi, M_FASTEST>;
   static thread_local int configured_dev = -1;  // per-instantiation, per-thread
   if (configured_dev != dev.device) {
     RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

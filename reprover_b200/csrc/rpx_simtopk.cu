@@ -1,0 +1,539 @@
+// rpx_simtopk.cu — fused similarity + top-k, the device half of
+// `Corpus.get_nearest_premises` (reference common.py:299-326):
+//     similarities = ctx_emb @ premise_emb.T        (:307)
+//     argsort(descending) ... first k accessible    (:308-322)
+//
+// Stage 1  sim_topk (gemm_tc_kernel<..., EpiSimTopk, M_FASTEST>):
+//   tcgen05 MMA of a 128-query block against 256-premise tiles streamed once from HBM
+//   by TMA; the [Q, N] score matrix is never written.  Each epilogue thread owns one
+//   query row in TMEM, compares its 256 scores against that query's running threshold
+//   and appends the few survivors (score, index) to a per-(CTA, query) candidate list.
+//   When a list fills up, the warp compacts it: a warp-shuffle bisection finds a
+//   threshold that keeps ~KEEP best entries, and the threshold rises.
+// Stage 2  select_rescore_kernel (one CTA per query):
+//   gathers the query's lists from the CTAs that served its block, selects the KEEP
+//   best by (fp32 score, index), re-scores those in fp64 with the canonical summation
+//   order (bf16 products are exact in fp64) and emits the k best ordered by
+//   (fp64 score desc, index asc) — the ordering contract in include/rpx.h.
+// Stage 3  topk_merge_kernel: the k-way merge after the multi-GPU all-gather.
+#include <math.h>
+
+#include "rpx_gemm_launch.cuh"
+#include "rpx_kernels.cuh"
+
+namespace rpx {
+
+namespace {
+
+constexpr int kSimBlockN = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Monotone map float bits -> uint32 (a > b  <=>  fkey(a) > fkey(b), -0 < +0).
+__device__ __forceinline__ uint32_t fkey(uint32_t u) { return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
+__device__ __forceinline__ uint32_t unkey(uint32_t k) { return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k; }
+
+// EPL = candidate entries per lane; a list holds CAP = 32*EPL entries and is compacted to
+// about KEEP = CAP/2.  KEEP is the size of the candidate superset handed to stage 2.
+template <int EPL>
+struct EpiSimTopk {
+  static constexpr int CAP = 32 * EPL;
+  static constexpr int KEEP = CAP / 2;
+  static constexpr int SLACK = 16;
+  struct Params {
+    uint2* cand;           // [grid][128][CAP]  (score bits, local index)
+    int32_t* cnt;          // [grid][128]
+    const uint32_t* mask;  // optional access bitmask [nq][mask_stride]
+    int64_t mask_stride;
+    int nq;
+    int n;
+    int tiles_m;
+  };
+  static constexpr size_t kSmemBytes = 0;
+
+  Params p;
+  float thr;
+  int cnt;
+  int q;
+  bool active;
+  uint2* warp_buf;  // list of lane 0's query; lane l's list is warp_buf + l*CAP
+  uint2* buf;
+  int lane;
+
+  __device__ EpiSimTopk(const Params& p_, uint8_t*, int row) : p(p_) {
+    lane = row & 31;
+    q = (blockIdx.x % p.tiles_m) * kBlockM + row;
+    active = q < p.nq;
+    thr = -INFINITY;
+    cnt = 0;
+    warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + (row & ~31)) * CAP;
+    buf = warp_buf + (size_t)lane * CAP;
+    slot = blockIdx.x * kBlockM + row;
+  }
+  int slot;
+
+  __device__ __forceinline__ void append(uint32_t bits, uint32_t idx) {
+    buf[cnt] = make_uint2(bits, idx);
+    ++cnt;
+  }
+
+  // Warp-cooperative compaction of every list in this warp that holds more than KEEP entries.
+  __device__ void compact_warp() {
+    for (int src = 0; src < 32; ++src) {
+      const int c = __shfl_sync(kFull, cnt, src);
+      if (c <= KEEP) continue;  // warp-uniform
+      uint2* b = warp_buf + (size_t)src * CAP;
+      uint2 e[EPL];
+      uint32_t key[EPL];
+      uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int pos = i * 32 + lane;
+        if (pos < c) {
+          e[i] = b[pos];
+          key[i] = fkey(e[i].x);
+          kmin = min(kmin, key[i]);
+          kmax = max(kmax, key[i]);
+        } else {
+          e[i] = make_uint2(0u, 0u);
+          key[i] = 0u;
+        }
+      }
+      kmin = __reduce_min_sync(kFull, kmin);
+      kmax = __reduce_max_sync(kFull, kmax);
+      // invariant: count(key >= lo) = count_lo >= KEEP ; count(key >= hi) < KEEP
+      uint64_t lo = kmin, hi = (uint64_t)kmax + 1;
+      int count_lo = c;
+      while (count_lo > KEEP + SLACK && hi - lo > 1) {
+        const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) m += (i * 32 + lane < c && key[i] >= mid) ? 1 : 0;
+        m = __reduce_add_sync(kFull, m);
+        if (m >= KEEP) {
+          lo = mid;
+          count_lo = m;
+        } else {
+          hi = mid;
+        }
+      }
+      const uint32_t lo32 = (uint32_t)lo;
+      const bool tie_mode = count_lo > KEEP + SLACK;  // > SLACK entries share the key `lo`
+      int need_eq = 0;
+      if (tie_mode) {
+        int gt = 0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) gt += (i * 32 + lane < c && key[i] > lo32) ? 1 : 0;
+        gt = __reduce_add_sync(kFull, gt);
+        need_eq = KEEP - gt;  // > 0 by the invariant (count(>= lo+1) < KEEP)
+      }
+      const unsigned lt_mask = (1u << lane) - 1u;
+      int out = 0, eq_seen = 0;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const bool valid = i * 32 + lane < c;
+        bool keep;
+        if (tie_mode) {
+          // lists are filled in increasing index order, so "first" == lowest index
+          const bool eq = valid && key[i] == lo32;
+          const unsigned eqb = __ballot_sync(kFull, eq);
+          keep = valid && (key[i] > lo32 || (eq && eq_seen + __popc(eqb & lt_mask) < need_eq));
+          eq_seen += __popc(eqb);
+        } else {
+          keep = valid && key[i] >= lo32;
+        }
+        const unsigned kb = __ballot_sync(kFull, keep);
+        if (keep) b[out + __popc(kb & lt_mask)] = e[i];
+        out += __popc(kb);
+      }
+      if (lane == src) {
+        cnt = out;
+        // pass rule is `score > thr`: ties of `lo` are shut out in tie mode (later ones have
+        // higher indices than the KEEP entries held), admitted otherwise.
+        thr = __uint_as_float(unkey(tie_mode ? lo32 : lo32 - 1u));
+      }
+    }
+    __syncwarp();
+  }
+
+  __device__ void tile(const TileCtx& t) {
+    for (int c = 0; c < t.n_cols; c += 32) {
+      if (__any_sync(kFull, cnt > CAP - 32)) compact_warp();
+      uint32_t v[32];
+      tmem_ld_32x32(t.tmem + c, v);
+      tmem_ld_wait();
+      const int base = t.n0 + c;
+      uint32_t word = 0xFFFFFFFFu;
+      if (p.mask != nullptr && active) word = p.mask[(size_t)q * p.mask_stride + (base >> 5)];
+      if (base + 32 > p.n) word &= (1u << (p.n - base)) - 1u;  // ragged corpus tail (n - base in 1..31)
+      if (!active) word = 0u;
+      if (word == 0xFFFFFFFFu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (__uint_as_float(v[j]) > thr) append(v[j], (uint32_t)(base + j));
+      } else if (word != 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (((word >> j) & 1u) && __uint_as_float(v[j]) > thr) append(v[j], (uint32_t)(base + j));
+      }
+    }
+  }
+
+  __device__ void finish() { p.cnt[slot] = cnt; }
+};
+
+// ------------------------------------------------------------------------------------ stage 2
+
+// Canonical fp64 dot product (identical in oracle/rpx_oracle.c::rpx_oracle_dot64):
+// lane l accumulates, in increasing j then e order, the elements d = (j*32 + l)*8 + e
+// (e = 0..7) with acc = fma(a, b, acc) — the bf16 x bf16 product is exact in fp64, so this is
+// one rounding per addition — and the 32 partials are combined by the xor butterfly
+// 16, 8, 4, 2, 1 (p = p + p_partner).
+__device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restrict__ qrow,  // smem or global
+                                                  const __nv_bfloat16* __restrict__ erow, int d, int lane) {
+  double acc = 0.0;
+  const int chunks = d >> 3;
+  for (int ch = lane; ch < chunks; ch += 32) {
+    const uint4 ev = *reinterpret_cast<const uint4*>(erow + ch * 8);
+    const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
+    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+    const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
+      const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
+      acc = fma(q0, e0, acc);
+      acc = fma(q1, e1, acc);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+  return acc;
+}
+
+constexpr int kSelThreads = 256;
+constexpr int kSelMax = 256 + 32;  // KEEP (<= 256) + selection slack
+
+__device__ __forceinline__ uint64_t ckey(uint2 e) {
+  // composite: score (monotone) high, ~index low => larger key == better under (score desc, index asc)
+  return ((uint64_t)fkey(e.x) << 32) | (uint64_t)(0xFFFFFFFFu - e.y);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity) {
+  for (int off = 16; off; off >>= 1) v = op(v, __shfl_xor_sync(kFull, v, off));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : identity;
+  if (threadIdx.x < 32) {
+    for (int off = 16; off; off >>= 1) r = op(r, __shfl_xor_sync(kFull, r, off));
+    if (threadIdx.x == 0) red[0] = r;
+  }
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int keep,
+                      int grid_sim, int tiles_m, const __nv_bfloat16* __restrict__ Q,
+                      const __nv_bfloat16* __restrict__ E, int d, int k, int64_t idx_offset,
+                      float* __restrict__ out_scores, double* __restrict__ out_scores64,
+                      int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_raw);                 // [d]
+  double* sel_score = reinterpret_cast<double*>(sm_raw + (((size_t)d * 2 + 15) & ~(size_t)15));  // [kSelMax]
+  uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_score + kSelMax);                           // [kSelMax]
+  __shared__ uint64_t red64[32];
+  __shared__ int redi[32];
+  __shared__ int n_sel;
+
+  const int q = blockIdx.x;
+  const int q_blk = q / kBlockM, row = q % kBlockM;
+  const int n_seg = grid_sim / tiles_m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < d / 8; i += kSelThreads)
+    reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(Q + (size_t)q * d)[i];
+  if (tid == 0) n_sel = 0;
+
+  // ---- bounds of the composite keys over all of this query's candidates
+  uint64_t kmin = ~0ull, kmax = 0ull;
+  int total = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const int slot = (q_blk + s * tiles_m) * kBlockM + row;
+    const int c = cnt[slot];
+    const uint2* b = cand + (size_t)slot * cap;
+    for (int i = tid; i < c; i += kSelThreads) {
+      const uint64_t key = ckey(b[i]);
+      kmin = key < kmin ? key : kmin;
+      kmax = key > kmax ? key : kmax;
+    }
+    total += c;
+  }
+  kmin = block_reduce<uint64_t>(kmin, red64, [](uint64_t a, uint64_t b) { return a < b ? a : b; }, ~0ull);
+  kmax = block_reduce<uint64_t>(kmax, red64, [](uint64_t a, uint64_t b) { return a > b ? a : b; }, 0ull);
+
+  // ---- threshold: count(key >= lo) in [keep, keep + 32] (keys are distinct, so it exists)
+  uint64_t lo = kmin;
+  if (total > keep + 32) {
+    uint64_t hi = kmax;  // count(>= kmax) = 1 < keep  (keep >= 2)
+    int count_lo = total;
+    // invariant: count(>= lo) = count_lo >= keep, count(>= hi) < keep
+    while (count_lo > keep + 32 && hi - lo > 1) {
+      const uint64_t mid = lo + (hi - lo) / 2;
+      int m = 0;
+      for (int s = 0; s < n_seg; ++s) {
+        const int slot = (q_blk + s * tiles_m) * kBlockM + row;
+        const int c = cnt[slot];
+        const uint2* b = cand + (size_t)slot * cap;
+        for (int i = tid; i < c; i += kSelThreads) m += ckey(b[i]) >= mid ? 1 : 0;
+      }
+      m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
+      if (m >= keep) {
+        lo = mid;
+        count_lo = m;
+      } else {
+        hi = mid;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- collect the selected candidates
+  for (int s = 0; s < n_seg; ++s) {
+    const int slot = (q_blk + s * tiles_m) * kBlockM + row;
+    const int c = cnt[slot];
+    const uint2* b = cand + (size_t)slot * cap;
+    for (int i = tid; i < c; i += kSelThreads) {
+      const uint2 e = b[i];
+      if (ckey(e) >= lo) {
+        const int pos = atomicAdd(&n_sel, 1);
+        if (pos < kSelMax) sel_idx[pos] = e.y;
+      }
+    }
+  }
+  __syncthreads();
+  const int ns = n_sel < kSelMax ? n_sel : kSelMax;
+
+  // ---- exact fp64 re-scoring, one warp per candidate
+  for (int c = warp; c < ns; c += kSelThreads / 32) {
+    const double s = dot64_canonical(sq, E + (size_t)sel_idx[c] * d, d, lane);
+    if (lane == 0) sel_score[c] = s;
+  }
+  __syncthreads();
+
+  // ---- rank by counting under (score desc, index asc); ranks are a permutation
+  for (int c = tid; c < ns; c += kSelThreads) {
+    const double sc = sel_score[c];
+    const uint32_t ic = sel_idx[c];
+    int rank = 0;
+    for (int j = 0; j < ns; ++j) {
+      const double sj = sel_score[j];
+      rank += (sj > sc || (sj == sc && sel_idx[j] < ic)) ? 1 : 0;
+    }
+    if (rank < k) {
+      const size_t o = (size_t)q * k + rank;
+      out_scores[o] = (float)sc;
+      if (out_scores64) out_scores64[o] = sc;
+      out_idx[o] = (int64_t)ic + idx_offset;
+    }
+  }
+  const int valid = ns < k ? ns : k;
+  for (int r = valid + tid; r < k; r += kSelThreads) {
+    const size_t o = (size_t)q * k + r;
+    out_scores[o] = -INFINITY;
+    if (out_scores64) out_scores64[o] = -INFINITY;
+    out_idx[o] = -1;
+  }
+  if (out_count && tid == 0) out_count[q] = valid;
+}
+
+// ------------------------------------------------------------------------------------ stage 3
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__ idx, int n_parts, int nq, int k,
+                  float* __restrict__ out_scores, double* __restrict__ out_scores64, int64_t* __restrict__ out_idx,
+                  int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int n = n_parts * k;
+  double* s = reinterpret_cast<double*>(sm_raw);
+  int64_t* ix = reinterpret_cast<int64_t*>(s + n);
+  __shared__ int n_valid;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) n_valid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int part = i / k, r = i % k;
+    const size_t src = ((size_t)part * nq + q) * k + r;
+    s[i] = scores[src];
+    ix[i] = idx[src];
+    local_valid += ix[i] >= 0 ? 1 : 0;
+  }
+  atomicAdd(&n_valid, local_valid);
+  __syncthreads();
+  for (int c = tid; c < n; c += blockDim.x) {
+    const int64_t ic = ix[c];
+    if (ic < 0) continue;
+    const double sc = s[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const int64_t ij = ix[j];
+      rank += (ij >= 0 && (s[j] > sc || (s[j] == sc && ij < ic))) ? 1 : 0;
+    }
+    if (rank < k) {
+      const size_t o = (size_t)q * k + rank;
+      out_scores[o] = (float)sc;
+      if (out_scores64) out_scores64[o] = sc;
+      out_idx[o] = ic;
+    }
+  }
+  const int valid = n_valid < k ? n_valid : k;
+  for (int r = valid + tid; r < k; r += blockDim.x) {
+    const size_t o = (size_t)q * k + r;
+    out_scores[o] = -INFINITY;
+    if (out_scores64) out_scores64[o] = -INFINITY;
+    out_idx[o] = -1;
+  }
+  if (out_count && tid == 0) out_count[q] = valid;
+}
+
+struct SimPlan {
+  int epl, cap, keep;
+  int tiles_m, grid;
+  size_t cand_bytes, cnt_bytes, total;
+};
+
+int plan_sim(int nq, int k, int num_sms, SimPlan* pl) {
+  RPX_REQUIRE(k >= 1 && k <= 200, RPX_ERR_UNSUPPORTED, "sim_topk: k=%d outside [1, 200]", k);
+  RPX_REQUIRE(nq >= 1, RPX_ERR_INVALID, "sim_topk: nq=%d", nq);
+  // candidate superset: k plus a margin (>= 28, >= k/4) that absorbs fp32-vs-fp64 rank flips
+  pl->epl = k <= 100 ? 8 : 16;
+  pl->cap = 32 * pl->epl;
+  pl->keep = pl->cap / 2;
+  int chunk_q = nq < num_sms * kBlockM ? nq : num_sms * kBlockM;  // queries per launch
+  pl->tiles_m = ceil_div(chunk_q, kBlockM);
+  pl->grid = (num_sms / pl->tiles_m) * pl->tiles_m;
+  pl->cand_bytes = align_up((size_t)pl->grid * kBlockM * pl->cap * sizeof(uint2), 256);
+  pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);
+  pl->total = pl->cand_bytes + pl->cnt_bytes;
+  return RPX_OK;
+}
+
+// Launch of stage 1 with the plan's (fixed) tiles_m / grid.  The A tensor map covers the true
+// nq rows, so query rows beyond nq are zero-filled by TMA and flagged inactive in the epilogue.
+template <int EPL>
+int launch_sim(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n, int d,
+               const typename EpiSimTopk<EPL>::Params& ep, const SimPlan& pl, cudaStream_t st) {
+  using Epi = EpiSimTopk<EPL>;
+  using Cfg = GemmCfg<kSimBlockN, kGemmStages>;
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  CUtensorMap tmA, tmB;
+  RPX_TRY(make_tmap_bf16_2d(&tmA, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, kBlockM));
+  RPX_TRY(make_tmap_bf16_2d(&tmB, E, (uint64_t)n, (uint64_t)d, (uint64_t)d, kSimBlockN));
+  const int tiles_n = (int)ceil_div64(n, kSimBlockN);
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  auto kern = gemm_tc_kernel<kSimBlockN, kGemmStages, Epi, true>;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev.device;
+  }
+  int64_t tiles = (int64_t)pl.tiles_m * tiles_n;
+  const int grid = tiles < pl.grid ? (int)tiles : pl.grid;  // stays a multiple of tiles_m
+  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, ep);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+}  // namespace
+}  // namespace rpx
+
+using namespace rpx;
+
+extern "C" {
+
+size_t rpx_sim_topk_workspace_bytes(int32_t nq, int32_t k) {
+  SimPlan pl;
+  // sized for the largest B200 SM count so the query works without a device
+  if (plan_sim(nq, k, 148, &pl) != RPX_OK) return 0;
+  SimPlan pl2;
+  if (plan_sim(nq, k, 160, &pl2) != RPX_OK) return 0;
+  return (pl.total > pl2.total ? pl.total : pl2.total) + 256;
+}
+
+int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_t d, int32_t k,
+                 const uint32_t* d_access_mask, int64_t mask_stride_words, float* d_out_scores,
+                 double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count, int64_t idx_offset,
+                 void* d_workspace, size_t workspace_bytes, void* stream) {
+  RPX_REQUIRE(d_Q && d_out_scores && d_out_idx && d_workspace, RPX_ERR_INVALID, "rpx_sim_topk: null argument");
+  RPX_REQUIRE(d_E != nullptr || n == 0, RPX_ERR_INVALID, "rpx_sim_topk: null index");
+  RPX_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX - 512, RPX_ERR_UNSUPPORTED, "rpx_sim_topk: n=%lld out of range", (long long)n);
+  RPX_REQUIRE(d > 0 && d % 64 == 0 && d <= 8192, RPX_ERR_UNSUPPORTED, "rpx_sim_topk: d=%d must be a multiple of 64 (<= 8192)", d);
+  RPX_REQUIRE(d_access_mask == nullptr || mask_stride_words * 32 >= n, RPX_ERR_INVALID, "rpx_sim_topk: mask stride too small");
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  SimPlan pl;
+  RPX_TRY(plan_sim(nq, k, dev.num_sms, &pl));
+  RPX_REQUIRE(pl.total <= workspace_bytes, RPX_ERR_WORKSPACE, "rpx_sim_topk: workspace %zu < %zu", workspace_bytes, pl.total);
+  RPX_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, RPX_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint2* cand = reinterpret_cast<uint2*>(d_workspace);
+  int32_t* cnt = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes);
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(d_Q);
+  const __nv_bfloat16* E = static_cast<const __nv_bfloat16*>(d_E);
+  const size_t sel_smem = (((size_t)d * 2 + 15) & ~(size_t)15) + kSelMax * (sizeof(double) + sizeof(uint32_t));
+  static thread_local int sel_configured = -1;
+  if (sel_configured != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    sel_configured = dev.device;
+  }
+  const int chunk_q = pl.tiles_m * kBlockM;
+  for (int q0 = 0; q0 < nq; q0 += chunk_q) {
+    const int nq_c = nq - q0 < chunk_q ? nq - q0 : chunk_q;
+    // (only the last chunk can be smaller; its tiles_m may shrink but the plan's grid stays valid
+    //  because we keep tiles_m fixed and let the surplus query blocks be empty)
+    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes, st));
+    const uint32_t* mask_c = d_access_mask ? d_access_mask + (size_t)q0 * mask_stride_words : nullptr;
+    if (n > 0) {
+      if (pl.epl == 8) {
+        EpiSimTopk<8>::Params ep{cand, cnt, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        // M is passed as tiles_m*128 so that tiles_m matches the plan; rows >= nq_c are inactive and
+        // their A rows are zero-filled by TMA (tensor map built on the true nq_c rows).
+        RPX_TRY((launch_sim<8>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+      } else {
+        EpiSimTopk<16>::Params ep{cand, cnt, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        RPX_TRY((launch_sim<16>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+      }
+    }
+    select_rescore_kernel<<<nq_c, kSelThreads, sel_smem, st>>>(
+        cand, cnt, pl.cap, pl.keep, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, idx_offset,
+        d_out_scores + (size_t)q0 * k, d_out_scores64 ? d_out_scores64 + (size_t)q0 * k : nullptr,
+        d_out_idx + (size_t)q0 * k, d_out_count ? d_out_count + q0 : nullptr);
+    RPX_CUDA_OK(cudaGetLastError());
+  }
+  return RPX_OK;
+}
+
+int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_parts, int32_t nq, int32_t k,
+                   float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count,
+                   void* stream) {
+  RPX_REQUIRE(d_scores64 && d_idx && d_out_scores && d_out_idx, RPX_ERR_INVALID, "rpx_topk_merge: null argument");
+  RPX_REQUIRE(n_parts >= 1 && nq >= 1 && k >= 1, RPX_ERR_INVALID, "rpx_topk_merge: bad sizes");
+  const size_t smem = (size_t)n_parts * k * 16;
+  RPX_REQUIRE(smem <= 96 * 1024, RPX_ERR_UNSUPPORTED, "rpx_topk_merge: n_parts*k=%d too large", n_parts * k);
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  static thread_local int configured = -1;
+  if (configured != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = dev.device;
+  }
+  topk_merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(d_scores64, d_idx, n_parts, nq, k, d_out_scores,
+                                                                       d_out_scores64, d_out_idx, d_out_count);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+}  // extern "C"
