@@ -1,0 +1,88 @@
+"""Row-sharded index across the GPUs of one box.
+
+The premise corpus splits row-wise into `world_size` contiguous shards; rank r owns
+rows [bounds[r], bounds[r+1]).  Re-indexing needs no communication (each rank
+encodes its shard).  Retrieval = local fused sim+top-k on every rank, ONE all-gather
+of the per-rank [Q, k] (fp64 score, int64 global index) pairs over NCCL/NVLink, and
+a device-side k-way merge with the same (score desc, index asc) comparator, so the
+result equals the single-GPU result on the concatenated index.
+
+The reference has no counterpart (single device, retrieval/confs/*.yaml `devices: 1`).
+The two compute steps are injectable so that the plumbing (bounds, offsets, gather
+layout) can be exercised on CPU with the `gloo` backend and the oracle as stand-in.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, world_size: int) -> List[int]:
+    """Contiguous, near-equal row ranges: bounds[r] .. bounds[r+1]."""
+    base, extra = divmod(n_rows, world_size)
+    bounds = [0]
+    for r in range(world_size):
+        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+    return bounds
+
+
+def _default_local_topk(queries, shard, k, idx_offset, access_mask):
+    from .retrieval_ops import sim_topk
+
+    s32, idx, cnt, s64 = sim_topk(queries, shard, k, access_mask=access_mask, idx_offset=idx_offset,
+                                  want_scores64=True)
+    return s64, idx
+
+
+def _default_merge(scores64, idx):
+    from .retrieval_ops import topk_merge
+
+    s32, mi, mc, ms64 = topk_merge(scores64, idx)
+    return s32, mi, mc, ms64
+
+
+def sharded_topk(queries: torch.Tensor, local_shard: torch.Tensor, k: int, row_offset: int,
+                 access_mask: Optional[torch.Tensor] = None, group=None,
+                 local_topk: Callable = _default_local_topk, merge: Callable = _default_merge):
+    """Global top-k over an index whose rows are spread over the ranks of `group`.
+
+    `queries` [Q, D] must be identical on every rank (replicated); `local_shard` is this rank's
+    rows, `row_offset` its first global row.  `access_mask`, if given, is this rank's slice of the
+    per-query bitmask (bit i of the slice <=> global row row_offset + i).  Every rank returns the
+    same (scores fp32 [Q,k], global indices int64 [Q,k], counts int32 [Q], scores fp64 [Q,k]).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    s64, idx = local_topk(queries, local_shard, k, row_offset, access_mask)
+    if world == 1:
+        return merge(s64.unsqueeze(0), idx.unsqueeze(0))
+    # one all-gather: pack (fp64 score bits, int64 index) into a single [Q, k, 2] int64 buffer
+    packed = torch.stack([s64.view(torch.int64), idx], dim=-1).contiguous()
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    all_s64 = gathered[..., 0].contiguous().view(torch.float64)
+    all_idx = gathered[..., 1].contiguous()
+    return merge(all_s64, all_idx)
+
+
+class ShardedIndex:
+    """This rank's slice of a row-sharded embedding index."""
+
+    def __init__(self, n_rows_total: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> None:
+        self.world_size = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
+        self.bounds = shard_bounds(n_rows_total, self.world_size)
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.embeddings: Optional[torch.Tensor] = None
+
+    def local_rows(self) -> range:
+        return range(self.lo, self.hi)
+
+    def set_embeddings(self, emb: torch.Tensor) -> None:
+        assert emb.shape[0] == self.hi - self.lo
+        self.embeddings = emb
+
+    def topk(self, queries: torch.Tensor, k: int, access_mask: Optional[torch.Tensor] = None, **kw):
+        assert self.embeddings is not None
+        return sharded_topk(queries, self.embeddings, k, self.lo, access_mask=access_mask, **kw)

@@ -1,0 +1,155 @@
+"""`B200PremiseRetriever` — drop-in for the inference surface of the reference's
+`PremiseRetriever` (retrieval/model.py:29): `load_hf`, `load_corpus`,
+`embedding_size`, `_encode`, `reindex_corpus`, `retrieve`, and the attributes its
+callers touch (`corpus`, `corpus_embeddings`, `embeddings_staled`, `device`,
+`max_seq_len`, `num_retrieved`).  Callers in the reference: `retrieval/index.py:33-38`,
+`prover/tactic_generator.py:271-292`, `generation/model.py:163-164,224-233`.
+
+Everything numeric is a call into the CUDA engine through the C ABI; torch only owns
+the buffers.  Training (`forward`, `training_step`, optimizers) is out of scope.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Any, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import tokenizer as byt5
+from .corpus import Context, Corpus, IndexedCorpus, Pos, Premise
+from .engine import T5EncoderEngine, load_hf_checkpoint
+
+
+class B200PremiseRetriever:
+    def __init__(self, model_name: str, lr: float = 0.0, warmup_steps: int = 0, max_seq_len: int = 2048,
+                 num_retrieved: int = 100, device: Union[int, str, torch.device, None] = None,
+                 dtype: Optional[torch.dtype] = None, max_tokens_per_call: int = 1 << 18) -> None:
+        """`model_name` is an HF checkpoint directory (config.json + model.safetensors)."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+        device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(
+                "B200PremiseRetriever runs on a B200 (sm_100a) only; there is no CPU path. "
+                "(The reference warns that CPU indexing is very slow, retrieval/index.py:28-30; this engine refuses.)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.lr = lr
+        self.warmup_steps = warmup_steps
+        self.num_retrieved = num_retrieved
+        self.max_seq_len = max_seq_len
+        self.device = device
+        # reference dtype policy (retrieval/model.py:56-66): bf16 on GPUs with cc >= 8 unless told otherwise.
+        # The engine always computes with bf16 operands / fp32 accumulation; `dtype` selects the dtype of
+        # the embeddings it hands back.
+        self.dtype = torch.bfloat16 if dtype is None else dtype
+        if self.dtype not in (torch.bfloat16, torch.float32):
+            raise NotImplementedError(f"embedding dtype {self.dtype} is not supported (bf16 or fp32)")
+        cfg, sd = load_hf_checkpoint(model_name)
+        self.encoder = T5EncoderEngine(cfg, sd, device, max_tokens_per_call=max_tokens_per_call)
+        self.corpus: Optional[Corpus] = None
+        self.corpus_embeddings: Optional[torch.Tensor] = None
+        self.embeddings_staled = True
+
+    # ------------------------------------------------------------------ construction (reference :52-85)
+    @classmethod
+    def load_hf(cls, ckpt_path: str, max_seq_len: int, device, dtype=None) -> "B200PremiseRetriever":
+        return cls(ckpt_path, 0.0, 0, max_seq_len, 100, device=device, dtype=dtype)
+
+    def load_corpus(self, path_or_corpus: Union[str, Corpus]) -> None:
+        """Attach a corpus: a `Corpus`, a `corpus.jsonl` path (stale index) or a pickled
+        `IndexedCorpus` (fresh index)."""
+        if isinstance(path_or_corpus, Corpus):
+            self.corpus = path_or_corpus
+            self.corpus_embeddings = None
+            self.embeddings_staled = True
+            return
+        path = path_or_corpus
+        if path.endswith(".jsonl"):
+            self.corpus = Corpus(path)
+            self.corpus_embeddings = None
+            self.embeddings_staled = True
+        else:
+            with open(path, "rb") as fh:
+                indexed = pickle.load(fh)
+            self.corpus = indexed.corpus
+            self.corpus_embeddings = indexed.embeddings
+            self.embeddings_staled = False
+
+    @property
+    def embedding_size(self) -> int:
+        return self.encoder.hidden_size
+
+    # ------------------------------------------------------------------ encode
+    def _encode(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        """Reference `_encode` (retrieval/model.py:92-114): [B, L] ids + mask -> [B, D] unit rows."""
+        return self.encoder.encode_ids(input_ids, attention_mask, out_dtype=self.dtype)
+
+    @torch.no_grad()
+    def encode_texts(self, texts: Sequence[str], batch_size: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tokenizer(...) + `_encode` for a list of strings (reference :199-206), rows in input order.
+
+        Strings without special-token literals (practically all Lean code) go to the device as raw
+        bytes; the rest are tokenised on the host with HF semantics and use the ids entry point."""
+        n = len(texts)
+        if out is None:
+            out = torch.empty(n, self.embedding_size, dtype=self.dtype, device=self.device)
+        plain = [i for i, t in enumerate(texts) if not byt5.needs_id_path(t)]
+        special = [i for i, t in enumerate(texts) if byt5.needs_id_path(t)]
+        if plain:
+            blobs = [texts[i].encode("utf-8") for i in plain]
+            if len(plain) == n:
+                self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype, out=out)
+            else:
+                emb = self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype)
+                out[torch.tensor(plain, device=self.device)] = emb
+        for lo in range(0, len(special), batch_size):
+            rows = special[lo:lo + batch_size]
+            ids, mask = byt5.pad_batch([byt5.encode_ids(texts[i], self.max_seq_len) for i in rows])
+            emb = self._encode(torch.from_numpy(ids).to(self.device), torch.from_numpy(mask).to(self.device))
+            out[torch.tensor(rows, device=self.device)] = emb
+        return out
+
+    @torch.no_grad()
+    def reindex_corpus(self, batch_size: int) -> None:
+        """Reference :183-210.  `batch_size` is kept for signature parity; the engine packs premises by
+        token budget instead (results do not depend on batching: padded keys have zero weight)."""
+        if not self.embeddings_staled:
+            return
+        assert self.corpus is not None, "load_corpus first"
+        texts = [p.serialize() for p in self.corpus.all_premises]
+        self.corpus_embeddings = torch.zeros(len(texts), self.embedding_size, dtype=self.dtype, device=self.device)
+        if texts:
+            self.encode_texts(texts, batch_size=batch_size, out=self.corpus_embeddings)
+        self.embeddings_staled = False
+
+    # ------------------------------------------------------------------ retrieve (reference :338-375)
+    @torch.no_grad()
+    def retrieve(self, state: str, file_name: str, theorem_full_name: str, theorem_pos: Any,
+                 k: int) -> Tuple[List[Premise], List[float]]:
+        premises, scores = self.retrieve_batch([state], [file_name], [theorem_full_name], [theorem_pos], k)
+        assert len(premises) == len(scores) == 1
+        return premises[0], scores[0]
+
+    @torch.no_grad()
+    def retrieve_batch(self, states: Sequence[str], file_names: Sequence[str], theorem_full_names: Sequence[str],
+                       theorem_poses: Sequence[Any], k: int) -> Tuple[List[List[Premise]], List[List[float]]]:
+        """Batched `retrieve` (what validation_step / predict_step do with Q = eval_batch_size,
+        reference :215-225, 281-289)."""
+        self.reindex_corpus(batch_size=32)
+        ctxs = [Context(f, t, Pos.from_any(p), s) for s, f, t, p in zip(states, file_names, theorem_full_names, theorem_poses)]
+        context_emb = self.encode_texts([c.serialize() for c in ctxs])
+        if self.corpus_embeddings.device != context_emb.device:
+            self.corpus_embeddings = self.corpus_embeddings.to(context_emb.device)
+        if self.corpus_embeddings.dtype != torch.bfloat16:
+            # the reference casts the index to the query dtype (bf16 on GPU) on first use (:363-366)
+            self.corpus_embeddings = self.corpus_embeddings.to(torch.bfloat16)
+        return self.corpus.get_nearest_premises(self.corpus_embeddings, ctxs, context_emb, k)
+
+    # ------------------------------------------------------------------ index I/O (reference retrieval/index.py:37-40)
+    def save_index(self, path: str) -> None:
+        assert self.corpus is not None and not self.embeddings_staled
+        with open(path, "wb") as fh:
+            pickle.dump(IndexedCorpus(self.corpus, self.corpus_embeddings.to(torch.float32).cpu()), fh)
