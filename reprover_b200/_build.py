@@ -23,9 +23,11 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
+# RPX_LIB_VARIANT=<name> selects a side-by-side build (tuning experiments: A/B on the same GPU box)
+_VARIANT = os.environ.get("RPX_LIB_VARIANT", "")
 LIB_DIR = PKG_DIR / "_lib"
-OBJ_DIR = LIB_DIR / "obj"
-LIB_PATH = LIB_DIR / "librpx.so"
+OBJ_DIR = LIB_DIR / ("obj_" + _VARIANT if _VARIANT else "obj")
+LIB_PATH = LIB_DIR / (f"librpx_{_VARIANT}.so" if _VARIANT else "librpx.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,6 +36,10 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+
+
+# extra defines for tuning experiments, e.g. RPX_NVCC_EXTRA="-DRPX_PREFETCH_KB=0"
+NVCC_FLAGS += [f for f in os.environ.get("RPX_NVCC_EXTRA", "").split() if f]
 
 
 def _nvcc() -> str:

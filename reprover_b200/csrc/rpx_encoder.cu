@@ -10,7 +10,7 @@
 //     h32  [T, D] fp32   residual stream (master copy)
 //     h16  [T, D] bf16   same values, GEMM A operand
 //     qkv  [T, 3*H*64] bf16,  attn [T, H*64] bf16,  ffn [T, d_ff] bf16
-//     ssA / ssB [6][T] fp32   per-row partial sums of h32^2 (one per 256-column output
+//     ssA / ssB [12][T] fp32  per-row partial sums of h32^2 (two per 256-column output
 //                             block of the GEMM that produced h32) -> RMSNorm row scale
 // RMSNorm never runs as its own kernel: its weight vector is folded into the next
 // GEMM's B operand when the weights are packed, and the row scale rsqrt(mean(h^2)+eps)
@@ -63,7 +63,7 @@ extern "C" int32_t rpx_t5_relative_bucket(int32_t relative_position, int32_t num
 struct rpx_encoder {
   rpx_t5_config cfg;
   int inner = 0;
-  int n_parts = 0;  // ceil(d_model / 256)
+  int n_parts = 0;  // RMSNorm partial sums per row: ceil(d_model / 256) * 2
   const float* emb = nullptr;
   const float* final_ln = nullptr;
   const float* bias_lut = nullptr;
@@ -289,7 +289,7 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
   RPX_REQUIRE(e != nullptr, RPX_ERR_INVALID, "out of host memory");
   e->cfg = *cfg;
   e->inner = inner;
-  e->n_parts = ceil_div(D, kBlockN);
+  e->n_parts = ceil_div(D, kBlockN) * (EpiResidual::kWarps / 4);
   auto fail = [&](int code) {
     delete e;
     return code;

@@ -31,8 +31,17 @@ namespace rpx {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+#ifndef RPX_PREFETCH_KB
+#define RPX_PREFETCH_KB 0
+#endif
+#ifndef RPX_EPI_WARPS
+#define RPX_EPI_WARPS 4
+#endif
+constexpr int kPrefetchKb = RPX_PREFETCH_KB;  // L2 prefetch distance of the streamed operand, in k-blocks (0 = off)
 constexpr int kEpiWarp0 = 2;  // first epilogue warp
+// threads of a launch: TMA warp + MMA warp + Epi::kWarps epilogue warps (4 or 8)
+template <class Epi>
+constexpr int gemm_threads() { return 64 + 32 * Epi::kWarps; }
 
 template <int BLOCK_N, int STAGES>
 struct GemmCfg {
@@ -57,16 +66,23 @@ struct TileCtx {
   int row;         // this thread's row inside the tile, 0..127
   int m_blk, n_blk;
   int M, N;
+  int next_m0, next_n0;  // origin of the next tile this CTA will process (next_m0 < 0: none)
+  int part, split;       // this warp handles the 32-column chunks with (chunk % split) == part
 };
 
 // Epi must provide:
 //   struct Params;                       (trivially copyable kernel argument)
 //   static constexpr size_t kSmemBytes;  (extra dynamic shared memory, may be 0)
-//   __device__ Epi(const Params&, uint8_t* smem_extra, int row /*tile row this thread owns, 0..127*/);
+//   static constexpr int kWarps;         (4 or 8 epilogue warps; with 8, two warps share a TMEM lane
+//                                         group and split the tile's 32-column chunks between them)
+//   __device__ Epi(const Params&, uint8_t* smem_extra, int row /*tile row this thread owns, 0..127*/,
+//                  int part /*column share of this warp, 0..kWarps/4-1*/);
+//   __device__ void before_wait(const TileCtx&);  (work that may run while the MMAs of this tile are
+//                                                  still in flight, e.g. prefetching)
 //   __device__ void tile(const TileCtx&);     (all 128 epilogue threads, warp-converged)
 //   __device__ void finish();
 template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int tiles_m, int tiles_n, typename Epi::Params ep) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
@@ -100,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], 128);
+        mbar_init(&tempty[s], 32 * Epi::kWarps);
       }
       fence_mbar_init();
     }
@@ -121,6 +137,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
+          // Optional (off by default, RPX_PREFETCH_KB): pull the streamed operand into L2 a few
+          // k-blocks ahead of its shared-memory load.  Measured on B200 (A/B on one box, round 1):
+          // distance 8 made every GEMM 6-12 % SLOWER, so it stays disabled.
+          if (kPrefetchKb == 0) {
+          } else if (kb + kPrefetchKb < num_kb) {
+            if (M_FASTEST) tma_prefetch_2d(&tmB, (kb + kPrefetchKb) * kBlockK, n_blk * BLOCK_N);
+            else tma_prefetch_2d(&tmA, (kb + kPrefetchKb) * kBlockK, m_blk * kBlockM);
+          } else {
+            const int nt = tile + gridDim.x;
+            if (nt < num_tiles) {
+              const int kb2 = kb + kPrefetchKb - num_kb;
+              if (kb2 < num_kb) {
+                if (M_FASTEST) tma_prefetch_2d(&tmB, kb2 * kBlockK, (nt / tiles_m) * BLOCK_N);
+                else tma_prefetch_2d(&tmA, kb2 * kBlockK, (nt / tiles_n) * kBlockM);
+              }
+            }
+          }
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK,
@@ -175,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue
     const int lane_grp = warp & 3;                            // TMEM lane group this warp may read
     const int row = lane_grp * 32 + (threadIdx.x & 31);       // row of the tile this thread owns
-    Epi epi(ep, smem_extra, row);
+    const int part = (warp - kEpiWarp0) >> 2;                 // which share of the columns (0 when 4 warps)
+    Epi epi(ep, smem_extra, row, part);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -188,9 +222,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (n_this > BLOCK_N) n_this = BLOCK_N;
       t.n_cols = n_this;
       t.row = row;
+      t.part = part;
+      t.split = Epi::kWarps / 4;
       t.M = M;
       t.N = N;
       t.tmem = tmem_base + as * BLOCK_N + ((uint32_t)(lane_grp * 32) << 16);
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < num_tiles) {
+          t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * kBlockM;
+          t.next_n0 = (M_FASTEST ? nt / tiles_m : nt % tiles_n) * BLOCK_N;
+        } else {
+          t.next_m0 = -1;
+          t.next_n0 = 0;
+        }
+      }
+      epi.before_wait(t);
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       epi.tile(t);
@@ -238,12 +285,14 @@ struct EpiStoreF32 {
     int ldc;
   };
   static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
-  __device__ EpiStoreF32(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ EpiStoreF32(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ void before_wait(const TileCtx&) {}
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
-    for (int c = 0; c < t.n_cols; c += 32) {
+    for (int c = 32 * t.part; c < t.n_cols; c += 32 * t.split) {
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
       tmem_ld_wait();
@@ -267,13 +316,15 @@ struct EpiStoreBF16 {
     RowScale rs;
   };
   static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
-  __device__ EpiStoreBF16(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ EpiStoreBF16(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ void before_wait(const TileCtx&) {}
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
     const float rs = ok ? p.rs.get(m) : 0.f;
-    for (int c = 0; c < t.n_cols; c += 32) {
+    for (int c = 32 * t.part; c < t.n_cols; c += 32 * t.split) {
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
       tmem_ld_wait();
@@ -295,55 +346,114 @@ struct EpiStoreBF16 {
 };
 
 // Residual update (attention output projection K8 and FFN down projection K9):
-//   h32[m, n] += acc;  h16[m, n] = bf16(h32[m, n]);  ss_out[n_blk][m] = sum_n h32[m, n]^2
+//   h32[m, n] += acc;  h16[m, n] = bf16(h32[m, n]);  ss_out[part-of-n_blk][m] = sum_n h32[m, n]^2
 // The fp32 copy is the residual stream; the bf16 copy is the next GEMM's A operand;
 // ss_out feeds the next RMSNorm (see RowScale).
+//
+// The accumulator arrives one ROW per thread (TMEM lane == thread), which is the worst
+// possible layout for global memory: a warp-wide 16-byte access would touch 32 different
+// 128-byte lines.  Each warp therefore transposes its 32x32 fp32 block through a swizzled
+// shared-memory tile and does the read-modify-write with lanes running along the row:
+// one instruction covers 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32).
+// Residual loads run one chunk ahead and the next tile's rows are prefetched into L2 one tile
+// ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting the chunks — was measured
+// neutral to slightly negative on B200 and is off by default.)
 struct EpiResidual {
   struct Params {
     float* h32;
     __nv_bfloat16* h16;
     int ld;
-    float* ss_out;  // [tiles_n][ss_stride]
+    float* ss_out;  // [tiles_n * 2][ss_stride]
     int ss_stride;
   };
-  static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = RPX_EPI_WARPS;
+  static constexpr size_t kSmemBytes = kWarps * 32 * 32 * sizeof(float);  // one 32x32 tile per warp
   Params p;
-  __device__ EpiResidual(const Params& p_, uint8_t*, int) : p(p_) {}
+  float4* stg;  // this warp's staging tile: row r = 8 float4, stored at slot (j ^ (r & 7))
+  int lane, grp;
+  __device__ EpiResidual(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
+    lane = row & 31;
+    grp = row >> 5;
+    stg = reinterpret_cast<float4*>(smem_extra) + (part * 4 + grp) * 32 * 8;
+  }
+  // Called right before this tile's accumulator is awaited: pull the residual rows of the NEXT
+  // tile into L2 now, so that by the time they are read-modify-written (one epilogue from now)
+  // the loads are L2 hits.  One 128-byte line per prefetch; row = lane.
+  __device__ void before_wait(const TileCtx& t) {
+    if (t.next_m0 < 0) return;
+    const int m = t.next_m0 + grp * 32 + lane;
+    if (m < t.M) {
+      const float* rowp = p.h32 + (size_t)m * p.ld + t.next_n0;
+      const int n_cols = t.N - t.next_n0 < 256 ? t.N - t.next_n0 : 256;
+      for (int c = 32 * t.part; c < n_cols; c += 32 * t.split)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + c));
+    }
+  }
+  __device__ __forceinline__ void load_chunk(const TileCtx& t, int c, int row_base, int sub, int col4,
+                                             float4 (&h)[8]) const {
+    const size_t col = (size_t)t.n0 + c + col4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = row_base + sub + 4 * i;
+      if (m < t.M) h[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
+      else h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   __device__ void tile(const TileCtx& t) {
-    const int m = t.m0 + t.row;
-    const bool ok = m < t.M;
-    float ss = 0.f;
-    for (int c = 0; c < t.n_cols; c += 32) {
+    const int sub = lane >> 3;        // row within a group of 4
+    const int j4 = lane & 7;          // which float4 of the 32-column chunk
+    const int col4 = j4 * 4;
+    const int row_base = t.m0 + grp * 32;
+    const int step = 32 * t.split;
+    float ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss[i] = 0.f;
+    float4 h[8], hn[8];
+    int c = 32 * t.part;
+    if (c < t.n_cols) load_chunk(t, c, row_base, sub, col4, h);
+    for (; c < t.n_cols; c += step) {
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
+      // next chunk's residual loads go out before this chunk is consumed
+      if (c + step < t.n_cols) load_chunk(t, c + step, row_base, sub, col4, hn);
+      const size_t col = (size_t)t.n0 + c + col4;
       tmem_ld_wait();
-      if (ok) {
-        float4* hp = reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + t.n0 + c);
-        uint4* bp = reinterpret_cast<uint4*>(p.h16 + (size_t)m * p.ld + t.n0 + c);
-        float4 h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = hp[i];
+      for (int j = 0; j < 8; ++j)
+        stg[lane * 8 + (j ^ (lane & 7))] =
+            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                        __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          h[i].x += __uint_as_float(v[4 * i + 0]);
-          h[i].y += __uint_as_float(v[4 * i + 1]);
-          h[i].z += __uint_as_float(v[4 * i + 2]);
-          h[i].w += __uint_as_float(v[4 * i + 3]);
-          ss += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
-          hp[i] = h[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack_bf16x2(h[2 * i].x, h[2 * i].y);
-          o.y = pack_bf16x2(h[2 * i].z, h[2 * i].w);
-          o.z = pack_bf16x2(h[2 * i + 1].x, h[2 * i + 1].y);
-          o.w = pack_bf16x2(h[2 * i + 1].z, h[2 * i + 1].w);
-          bp[i] = o;
+      for (int i = 0; i < 8; ++i) {
+        const int r = sub + 4 * i;
+        const int m = row_base + r;
+        const float4 a = stg[r * 8 + (j4 ^ (r & 7))];
+        h[i].x += a.x;
+        h[i].y += a.y;
+        h[i].z += a.z;
+        h[i].w += a.w;
+        ss[i] += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
+        if (m < t.M) {
+          *reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + col) = h[i];
+          *reinterpret_cast<uint2*>(p.h16 + (size_t)m * p.ld + col) =
+              make_uint2(pack_bf16x2(h[i].x, h[i].y), pack_bf16x2(h[i].z, h[i].w));
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = hn[i];
     }
-    if (ok) p.ss_out[(size_t)t.n_blk * p.ss_stride + m] = ss;
+    // a row's partial sums sit in the 8 lanes that share `sub`
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 4);
+      const int m = row_base + sub + 4 * i;
+      if ((lane & 7) == 0 && m < t.M)
+        p.ss_out[(size_t)(t.n_blk * t.split + t.part) * p.ss_stride + m] = ss[i];
+    }
   }
   __device__ void finish() {}
 };
@@ -369,13 +479,15 @@ struct EpiGeGLU {
     RowScale rs;
   };
   static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
-  __device__ EpiGeGLU(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ EpiGeGLU(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ void before_wait(const TileCtx&) {}
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
     const float rs = ok ? p.rs.get(m) : 0.f;
-    for (int c = 0; c < 128; c += 32) {
+    for (int c = 32 * t.part; c < 128; c += 32 * t.split) {
       uint32_t g[32], u[32];
       tmem_ld_32x32(t.tmem + c, g);
       tmem_ld_32x32(t.tmem + 128 + c, u);

@@ -64,15 +64,22 @@ RPX_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok;
 }
-// Bounded wait.  `tag` identifies the call site in the trap message.
+// Bounded wait.  `tag` identifies the call site in the trap message.  try_wait suspends the
+// thread in hardware for a bounded time, so the loop body is kept to the bare minimum: these
+// single-thread spin loops share their SM sub-partition's issue slots with an epilogue warp.
 RPX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug, not a slow kernel
-      printf("[rpx] mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
-             (int)threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0x3FFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {  // ~2 s: a pipeline bug, not a slow kernel
+        printf("[rpx] mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+               (int)threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -99,6 +106,13 @@ RPX_DEVICE void tma_load_2d_hint(void* smem_dst, const void* tmap, uint64_t* bar
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
         "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+// L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking).
+RPX_DEVICE void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -32,16 +32,19 @@ constexpr unsigned kFull = 0xffffffffu;
 __device__ __forceinline__ uint32_t fkey(uint32_t u) { return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
 __device__ __forceinline__ uint32_t unkey(uint32_t k) { return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k; }
 
-// EPL = candidate entries per lane; a list holds CAP = 32*EPL entries and is compacted to
-// about KEEP = CAP/2.  KEEP is the size of the candidate superset handed to stage 2.
-template <int EPL>
+// EPL = candidate entries per lane: a list holds CAP = 32*EPL entries and is compacted back to
+// about KEEP (<= CAP/2) when it fills.  KEEP is the size of the candidate superset a CTA
+// guarantees for its slice of the corpus.
+template <int EPL, int KEEP_>
 struct EpiSimTopk {
   static constexpr int CAP = 32 * EPL;
-  static constexpr int KEEP = CAP / 2;
+  static constexpr int KEEP = KEEP_;
   static constexpr int SLACK = 16;
+  static_assert(KEEP + SLACK + 32 <= CAP, "list too small");
   struct Params {
     uint2* cand;           // [grid][128][CAP]  (score bits, local index)
     int32_t* cnt;          // [grid][128]
+    uint32_t* gthr;        // [tiles_m*128] shared per-query threshold (monotone key, atomicMax)
     const uint32_t* mask;  // optional access bitmask [nq][mask_stride]
     int64_t mask_stride;
     int nq;
@@ -49,38 +52,65 @@ struct EpiSimTopk {
     int tiles_m;
   };
   static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = 4;  // one warp per TMEM lane group: a query's list has one writer
 
   Params p;
-  float thr;
-  int cnt;
-  int q;
-  bool active;
+  float thr;        // pass rule: score > thr
+  uint2* wptr;      // next free entry of this thread's list
+  uint2* buf;       // this thread's (query's) list
   uint2* warp_buf;  // list of lane 0's query; lane l's list is warp_buf + l*CAP
-  uint2* buf;
-  int lane;
+  int q, lane, slot;
+  bool active;
 
-  __device__ EpiSimTopk(const Params& p_, uint8_t*, int row) : p(p_) {
+  __device__ EpiSimTopk(const Params& p_, uint8_t*, int row, int) : p(p_) {
     lane = row & 31;
     q = (blockIdx.x % p.tiles_m) * kBlockM + row;
     active = q < p.nq;
     thr = -INFINITY;
-    cnt = 0;
     warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + (row & ~31)) * CAP;
     buf = warp_buf + (size_t)lane * CAP;
+    wptr = buf;
     slot = blockIdx.x * kBlockM + row;
   }
-  int slot;
+  __device__ __forceinline__ int count() const { return (int)(wptr - buf); }
 
-  __device__ __forceinline__ void append(uint32_t bits, uint32_t idx) {
-    buf[cnt] = make_uint2(bits, idx);
-    ++cnt;
+  // Branch-free conditional append: every lane executes the same three instructions, the store
+  // and the pointer bump are predicated.  (A branchy append serialises the warp once per lane
+  // that appends, which made the epilogue ~4x slower than the MMA it has to keep up with.)
+  __device__ __forceinline__ void append_if_gt(uint32_t bits, uint32_t idx) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f32 p, %1, %2;\n"
+        "@p st.global.v2.b32 [%0], {%3, %4};\n"
+        "@p add.s64 %0, %0, 8;\n"
+        "}\n"
+        : "+l"(wptr)
+        : "f"(__uint_as_float(bits)), "f"(thr), "r"(bits), "r"(idx)
+        : "memory");
+  }
+  __device__ __forceinline__ void append_if_gt_masked(uint32_t bits, uint32_t idx, uint32_t bit) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f32 p, %1, %2;\n"
+        "setp.ne.and.u32 p, %5, 0, p;\n"
+        "@p st.global.v2.b32 [%0], {%3, %4};\n"
+        "@p add.s64 %0, %0, 8;\n"
+        "}\n"
+        : "+l"(wptr)
+        : "f"(__uint_as_float(bits)), "f"(thr), "r"(bits), "r"(idx), "r"(bit)
+        : "memory");
   }
 
-  // Warp-cooperative compaction of every list in this warp that holds more than KEEP entries.
-  __device__ void compact_warp() {
+  // Warp-cooperative compaction of every list in this warp that holds more than `min_count`
+  // entries: a bisection over the monotone score keys finds a threshold that keeps between KEEP
+  // and KEEP+SLACK entries (exactly KEEP, lowest indices first, when many scores tie).
+  __device__ void compact_warp(int min_count) {
+    const int my_cnt = count();
     for (int src = 0; src < 32; ++src) {
-      const int c = __shfl_sync(kFull, cnt, src);
-      if (c <= KEEP) continue;  // warp-uniform
+      const int c = __shfl_sync(kFull, my_cnt, src);
+      if (c <= min_count) continue;  // warp-uniform
       uint2* b = warp_buf + (size_t)src * CAP;
       uint2 e[EPL];
       uint32_t key[EPL];
@@ -146,18 +176,28 @@ struct EpiSimTopk {
         out += __popc(kb);
       }
       if (lane == src) {
-        cnt = out;
+        wptr = buf + out;
         // pass rule is `score > thr`: ties of `lo` are shut out in tie mode (later ones have
         // higher indices than the KEEP entries held), admitted otherwise.
-        thr = __uint_as_float(unkey(tie_mode ? lo32 : lo32 - 1u));
+        const float t_new = __uint_as_float(unkey(tie_mode ? lo32 : lo32 - 1u));
+        thr = fmaxf(thr, t_new);
+        // This CTA holds >= KEEP entries with key >= lo, so no entry with key < lo can be in the
+        // query's global top-KEEP: publish the bound for the other CTAs serving this query block.
+        atomicMax(p.gthr + q, lo32 - 1u);
       }
     }
     __syncwarp();
   }
 
+  __device__ void before_wait(const TileCtx&) {}
   __device__ void tile(const TileCtx& t) {
+    // adopt the best bound any CTA of this query block has published so far
+    if (active) {
+      const uint32_t g = __ldcg(p.gthr + q);
+      if (g > fkey(__float_as_uint(thr))) thr = __uint_as_float(unkey(g));
+    }
     for (int c = 0; c < t.n_cols; c += 32) {
-      if (__any_sync(kFull, cnt > CAP - 32)) compact_warp();
+      if (__any_sync(kFull, count() > CAP - 32)) compact_warp(KEEP);
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
       tmem_ld_wait();
@@ -166,19 +206,21 @@ struct EpiSimTopk {
       if (p.mask != nullptr && active) word = p.mask[(size_t)q * p.mask_stride + (base >> 5)];
       if (base + 32 > p.n) word &= (1u << (p.n - base)) - 1u;  // ragged corpus tail (n - base in 1..31)
       if (!active) word = 0u;
-      if (word == 0xFFFFFFFFu) {
+      if (__all_sync(kFull, word == 0xFFFFFFFFu)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (__uint_as_float(v[j]) > thr) append(v[j], (uint32_t)(base + j));
-      } else if (word != 0u) {
+        for (int j = 0; j < 32; ++j) append_if_gt(v[j], (uint32_t)(base + j));
+      } else if (__any_sync(kFull, word != 0u)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (((word >> j) & 1u) && __uint_as_float(v[j]) > thr) append(v[j], (uint32_t)(base + j));
+        for (int j = 0; j < 32; ++j) append_if_gt_masked(v[j], (uint32_t)(base + j), (word >> j) & 1u);
       }
     }
   }
 
-  __device__ void finish() { p.cnt[slot] = cnt; }
+  __device__ void finish() {
+    // hand stage 2 short lists
+    if (__any_sync(kFull, count() > KEEP + SLACK)) compact_warp(KEEP + SLACK);
+    p.cnt[slot] = count();
+  }
 };
 
 // ------------------------------------------------------------------------------------ stage 2
@@ -211,7 +253,7 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
 }
 
 constexpr int kSelThreads = 256;
-constexpr int kSelMax = 256 + 32;  // KEEP (<= 256) + selection slack
+constexpr int kSelMax = 288;  // >= largest re-score set (k + margin + selection slack)
 
 __device__ __forceinline__ uint64_t ckey(uint2 e) {
   // composite: score (monotone) high, ~index low => larger key == better under (score desc, index asc)
@@ -235,63 +277,74 @@ __device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity) {
   return r;
 }
 
+// One CTA per query.  The query's candidate lists (one per stage-1 CTA that served its block,
+// each <= list_max entries) are staged in shared memory as 64-bit composite keys; a bisection
+// picks the `n_res` best (+ <= 16), which are re-scored in fp64 and ranked exactly.
 __global__ void __launch_bounds__(kSelThreads)
-select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int keep,
-                      int grid_sim, int tiles_m, const __nv_bfloat16* __restrict__ Q,
+select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int list_max,
+                      int n_res, int grid_sim, int tiles_m, const __nv_bfloat16* __restrict__ Q,
                       const __nv_bfloat16* __restrict__ E, int d, int k, int64_t idx_offset,
                       float* __restrict__ out_scores, double* __restrict__ out_scores64,
                       int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_raw);                 // [d]
-  double* sel_score = reinterpret_cast<double*>(sm_raw + (((size_t)d * 2 + 15) & ~(size_t)15));  // [kSelMax]
-  uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_score + kSelMax);                           // [kSelMax]
+  const int n_seg = grid_sim / tiles_m;
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_raw);                                  // [d]
+  double* sel_score = reinterpret_cast<double*>(sm_raw + (((size_t)d * 2 + 15) & ~(size_t)15));   // [kSelMax]
+  uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_score + kSelMax);                            // [kSelMax]
+  int* seg_off = reinterpret_cast<int*>(sel_idx + kSelMax);                                        // [n_seg + 1]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(seg_off + n_seg + 1) + 15) & ~(uintptr_t)15);                   // [n_seg * list_max]
   __shared__ uint64_t red64[32];
   __shared__ int redi[32];
   __shared__ int n_sel;
 
   const int q = blockIdx.x;
   const int q_blk = q / kBlockM, row = q % kBlockM;
-  const int n_seg = grid_sim / tiles_m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < d / 8; i += kSelThreads)
     reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(Q + (size_t)q * d)[i];
-  if (tid == 0) n_sel = 0;
+  if (tid == 0) {
+    n_sel = 0;
+    int acc = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      seg_off[s] = acc;
+      int c = cnt[(q_blk + s * tiles_m) * kBlockM + row];
+      acc += c < list_max ? c : list_max;  // (stage 1 guarantees c <= list_max)
+    }
+    seg_off[n_seg] = acc;
+  }
+  __syncthreads();
+  const int total = seg_off[n_seg];
 
-  // ---- bounds of the composite keys over all of this query's candidates
+  // ---- stage the composite keys
   uint64_t kmin = ~0ull, kmax = 0ull;
-  int total = 0;
-  for (int s = 0; s < n_seg; ++s) {
+  for (int s = warp; s < n_seg; s += kSelThreads / 32) {
     const int slot = (q_blk + s * tiles_m) * kBlockM + row;
-    const int c = cnt[slot];
+    const int o = seg_off[s], c = seg_off[s + 1] - o;
     const uint2* b = cand + (size_t)slot * cap;
-    for (int i = tid; i < c; i += kSelThreads) {
+    for (int i = lane; i < c; i += 32) {
       const uint64_t key = ckey(b[i]);
+      keys[o + i] = key;
       kmin = key < kmin ? key : kmin;
       kmax = key > kmax ? key : kmax;
     }
-    total += c;
   }
   kmin = block_reduce<uint64_t>(kmin, red64, [](uint64_t a, uint64_t b) { return a < b ? a : b; }, ~0ull);
   kmax = block_reduce<uint64_t>(kmax, red64, [](uint64_t a, uint64_t b) { return a > b ? a : b; }, 0ull);
 
-  // ---- threshold: count(key >= lo) in [keep, keep + 32] (keys are distinct, so it exists)
+  // ---- threshold: count(key >= lo) in [n_res, n_res + 16] (keys are distinct, so it exists)
   uint64_t lo = kmin;
-  if (total > keep + 32) {
-    uint64_t hi = kmax;  // count(>= kmax) = 1 < keep  (keep >= 2)
+  if (total > n_res + 16) {
+    uint64_t hi = kmax;  // count(>= kmax) = 1 < n_res
     int count_lo = total;
-    // invariant: count(>= lo) = count_lo >= keep, count(>= hi) < keep
-    while (count_lo > keep + 32 && hi - lo > 1) {
+    // invariant: count(>= lo) = count_lo >= n_res, count(>= hi) < n_res
+    while (count_lo > n_res + 16 && hi - lo > 1) {
       const uint64_t mid = lo + (hi - lo) / 2;
       int m = 0;
-      for (int s = 0; s < n_seg; ++s) {
-        const int slot = (q_blk + s * tiles_m) * kBlockM + row;
-        const int c = cnt[slot];
-        const uint2* b = cand + (size_t)slot * cap;
-        for (int i = tid; i < c; i += kSelThreads) m += ckey(b[i]) >= mid ? 1 : 0;
-      }
+      for (int i = tid; i < total; i += kSelThreads) m += keys[i] >= mid ? 1 : 0;
       m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
-      if (m >= keep) {
+      if (m >= n_res) {
         lo = mid;
         count_lo = m;
       } else {
@@ -299,18 +352,12 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
       }
     }
   }
-  __syncthreads();
   // ---- collect the selected candidates
-  for (int s = 0; s < n_seg; ++s) {
-    const int slot = (q_blk + s * tiles_m) * kBlockM + row;
-    const int c = cnt[slot];
-    const uint2* b = cand + (size_t)slot * cap;
-    for (int i = tid; i < c; i += kSelThreads) {
-      const uint2 e = b[i];
-      if (ckey(e) >= lo) {
-        const int pos = atomicAdd(&n_sel, 1);
-        if (pos < kSelMax) sel_idx[pos] = e.y;
-      }
+  for (int i = tid; i < total; i += kSelThreads) {
+    const uint64_t key = keys[i];
+    if (key >= lo) {
+      const int pos = atomicAdd(&n_sel, 1);
+      if (pos < kSelMax) sel_idx[pos] = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
     }
   }
   __syncthreads();
@@ -399,33 +446,49 @@ topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__
 }
 
 struct SimPlan {
-  int epl, cap, keep;
+  int epl, cap, keep, list_max, n_res;
+  size_t sel_smem;
   int tiles_m, grid;
-  size_t cand_bytes, cnt_bytes, total;
+  size_t cand_bytes, cnt_bytes, gthr_bytes, total;
 };
 
-int plan_sim(int nq, int k, int num_sms, SimPlan* pl) {
+constexpr size_t kSelSmemBudget = 200 * 1024;
+
+size_t sel_smem_bytes(int d, int n_seg, int list_max) {
+  return (((size_t)d * 2 + 15) & ~(size_t)15) + kSelMax * (sizeof(double) + sizeof(uint32_t)) +
+         ((size_t)n_seg + 1) * sizeof(int) + 16 + (size_t)n_seg * list_max * sizeof(uint64_t);
+}
+
+int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
   RPX_REQUIRE(k >= 1 && k <= 200, RPX_ERR_UNSUPPORTED, "sim_topk: k=%d outside [1, 200]", k);
   RPX_REQUIRE(nq >= 1, RPX_ERR_INVALID, "sim_topk: nq=%d", nq);
-  // candidate superset: k plus a margin (>= 28, >= k/4) that absorbs fp32-vs-fp64 rank flips
-  pl->epl = k <= 100 ? 8 : 16;
+  // per-CTA candidate superset KEEP >= re-score set n_res = k + margin; the margin absorbs
+  // fp32 (tensor-core) vs fp64 rank flips at the k-th place
+  pl->n_res = k + (k / 8 > 12 ? k / 8 : 12);
+  pl->keep = k <= 100 ? 128 : 256;
+  pl->epl = 16;
   pl->cap = 32 * pl->epl;
-  pl->keep = pl->cap / 2;
+  pl->list_max = pl->keep + 16;
   int chunk_q = nq < num_sms * kBlockM ? nq : num_sms * kBlockM;  // queries per launch
   pl->tiles_m = ceil_div(chunk_q, kBlockM);
-  pl->grid = (num_sms / pl->tiles_m) * pl->tiles_m;
+  int n_seg = num_sms / pl->tiles_m;
+  // stage 2 keeps one query's lists in shared memory
+  while (n_seg > 1 && sel_smem_bytes(d, n_seg, pl->list_max) > kSelSmemBudget) --n_seg;
+  pl->grid = n_seg * pl->tiles_m;
+  pl->sel_smem = sel_smem_bytes(d, n_seg, pl->list_max);
   pl->cand_bytes = align_up((size_t)pl->grid * kBlockM * pl->cap * sizeof(uint2), 256);
   pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);
-  pl->total = pl->cand_bytes + pl->cnt_bytes;
+  pl->gthr_bytes = align_up((size_t)pl->tiles_m * kBlockM * sizeof(uint32_t), 256);
+  pl->total = pl->cand_bytes + pl->cnt_bytes + pl->gthr_bytes;
   return RPX_OK;
 }
 
 // Launch of stage 1 with the plan's (fixed) tiles_m / grid.  The A tensor map covers the true
 // nq rows, so query rows beyond nq are zero-filled by TMA and flagged inactive in the epilogue.
-template <int EPL>
+template <int EPL, int KEEP>
 int launch_sim(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n, int d,
-               const typename EpiSimTopk<EPL>::Params& ep, const SimPlan& pl, cudaStream_t st) {
-  using Epi = EpiSimTopk<EPL>;
+               const typename EpiSimTopk<EPL, KEEP>::Params& ep, const SimPlan& pl, cudaStream_t st) {
+  using Epi = EpiSimTopk<EPL, KEEP>;
   using Cfg = GemmCfg<kSimBlockN, kGemmStages>;
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
@@ -442,7 +505,7 @@ int launch_sim(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n
   }
   int64_t tiles = (int64_t)pl.tiles_m * tiles_n;
   const int grid = tiles < pl.grid ? (int)tiles : pl.grid;  // stays a multiple of tiles_m
-  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, ep);
+  kern<<<grid, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, ep);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }
@@ -456,11 +519,10 @@ extern "C" {
 
 size_t rpx_sim_topk_workspace_bytes(int32_t nq, int32_t k) {
   SimPlan pl;
-  // sized for the largest B200 SM count so the query works without a device
-  if (plan_sim(nq, k, 148, &pl) != RPX_OK) return 0;
-  SimPlan pl2;
-  if (plan_sim(nq, k, 160, &pl2) != RPX_OK) return 0;
-  return (pl.total > pl2.total ? pl.total : pl2.total) + 256;
+  // sized for the largest Blackwell SM count so the query works without a device (d only
+  // shrinks the plan, so the smallest legal d gives the upper bound)
+  if (plan_sim(nq, k, 64, 160, &pl) != RPX_OK) return 0;
+  return pl.total + 256;
 }
 
 int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_t d, int32_t k,
@@ -475,18 +537,19 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   SimPlan pl;
-  RPX_TRY(plan_sim(nq, k, dev.num_sms, &pl));
+  RPX_TRY(plan_sim(nq, k, d, dev.num_sms, &pl));
   RPX_REQUIRE(pl.total <= workspace_bytes, RPX_ERR_WORKSPACE, "rpx_sim_topk: workspace %zu < %zu", workspace_bytes, pl.total);
   RPX_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, RPX_ERR_INVALID, "workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint2* cand = reinterpret_cast<uint2*>(d_workspace);
   int32_t* cnt = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes);
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes + pl.cnt_bytes);
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(d_Q);
   const __nv_bfloat16* E = static_cast<const __nv_bfloat16*>(d_E);
-  const size_t sel_smem = (((size_t)d * 2 + 15) & ~(size_t)15) + kSelMax * (sizeof(double) + sizeof(uint32_t));
   static thread_local int sel_configured = -1;
   if (sel_configured != dev.device) {
-    RPX_CUDA_OK(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    RPX_CUDA_OK(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(kSelSmemBudget + 8 * 1024)));
     sel_configured = dev.device;
   }
   const int chunk_q = pl.tiles_m * kBlockM;
@@ -494,21 +557,19 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
     const int nq_c = nq - q0 < chunk_q ? nq - q0 : chunk_q;
     // (only the last chunk can be smaller; its tiles_m may shrink but the plan's grid stays valid
     //  because we keep tiles_m fixed and let the surplus query blocks be empty)
-    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes, st));
+    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + pl.gthr_bytes, st));  // cnt and gthr are adjacent
     const uint32_t* mask_c = d_access_mask ? d_access_mask + (size_t)q0 * mask_stride_words : nullptr;
     if (n > 0) {
-      if (pl.epl == 8) {
-        EpiSimTopk<8>::Params ep{cand, cnt, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
-        // M is passed as tiles_m*128 so that tiles_m matches the plan; rows >= nq_c are inactive and
-        // their A rows are zero-filled by TMA (tensor map built on the true nq_c rows).
-        RPX_TRY((launch_sim<8>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+      if (pl.keep == 128) {
+        EpiSimTopk<16, 128>::Params ep{cand, cnt, gthr, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        RPX_TRY((launch_sim<16, 128>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       } else {
-        EpiSimTopk<16>::Params ep{cand, cnt, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
-        RPX_TRY((launch_sim<16>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+        EpiSimTopk<16, 256>::Params ep{cand, cnt, gthr, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        RPX_TRY((launch_sim<16, 256>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       }
     }
-    select_rescore_kernel<<<nq_c, kSelThreads, sel_smem, st>>>(
-        cand, cnt, pl.cap, pl.keep, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, idx_offset,
+    select_rescore_kernel<<<nq_c, kSelThreads, pl.sel_smem, st>>>(
+        cand, cnt, pl.cap, pl.list_max, pl.n_res, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, idx_offset,
         d_out_scores + (size_t)q0 * k, d_out_scores64 ? d_out_scores64 + (size_t)q0 * k : nullptr,
         d_out_idx + (size_t)q0 * k, d_out_count ? d_out_count + q0 : nullptr);
     RPX_CUDA_OK(cudaGetLastError());
