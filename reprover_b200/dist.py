@@ -59,8 +59,11 @@ def sharded_topk(queries: torch.Tensor, local_shard: torch.Tensor, k: int, row_o
         return merge(s64.unsqueeze(0), idx.unsqueeze(0))
     # one all-gather: pack (fp64 score bits, int64 index) into a single [Q, k, 2] int64 buffer
     packed = torch.stack([s64.view(torch.int64), idx], dim=-1).contiguous()
-    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=packed.device)
+    # (concatenated-along-dim-0 output: the layout both NCCL and gloo accept)
+    gathered = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=torch.int64,
+                           device=packed.device)
     dist.all_gather_into_tensor(gathered, packed, group=group)
+    gathered = gathered.view((world,) + tuple(packed.shape))
     all_s64 = gathered[..., 0].contiguous().view(torch.float64)
     all_idx = gathered[..., 1].contiguous()
     return merge(all_s64, all_idx)

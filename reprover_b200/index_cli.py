@@ -1,0 +1,41 @@
+"""Index a corpus with the B200 engine.  Same flags and output format as the reference's
+`retrieval/index.py` (--ckpt_path, --corpus-path, --output-path, --batch-size; writes a pickled
+`IndexedCorpus` with fp32 CPU embeddings, retrieval/index.py:33-40), so the result can be
+handed to anything that calls `load_corpus(indexed_corpus_path)`.
+
+    python -m reprover_b200.index_cli --ckpt_path <hf dir> --corpus-path corpus.jsonl --output-path index.pickle
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+
+import torch
+
+from .retriever import B200PremiseRetriever
+
+logger = logging.getLogger("reprover_b200.index")
+
+
+def main(argv=None) -> None:
+    parser = argparse.ArgumentParser(description="Index a premise corpus with the B200 retrieval engine.")
+    parser.add_argument("--ckpt_path", type=str, required=True)
+    parser.add_argument("--corpus-path", type=str, required=True)
+    parser.add_argument("--output-path", type=str, required=True)
+    parser.add_argument("--batch-size", type=int, default=64)
+    parser.add_argument("--max-seq-len", type=int, default=2048)  # the reference hard-codes 2048 (index.py:33)
+    args = parser.parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    logger.info(args)
+    if not torch.cuda.is_available():
+        # the reference falls back to the CPU with a warning (index.py:28-30); this engine does not
+        raise SystemExit("reprover_b200 needs a B200 GPU: there is no CPU indexing path")
+    model = B200PremiseRetriever.load_hf(args.ckpt_path, args.max_seq_len, torch.device("cuda"))
+    model.load_corpus(args.corpus_path)
+    model.reindex_corpus(batch_size=args.batch_size)
+    model.save_index(args.output_path)
+    logger.info("Indexed corpus saved to %s", args.output_path)
+
+
+if __name__ == "__main__":
+    main()

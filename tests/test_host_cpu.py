@@ -1,0 +1,176 @@
+"""Host-side logic of the drop-in surface (no GPU): tokenizer mirror, corpus data model and
+accessibility masks, synthetic data, shard bounds."""
+import json
+import pickle
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as ref
+from reprover_b200 import synth
+from reprover_b200 import tokenizer as byt5
+from reprover_b200.corpus import Context, Corpus, File, IndexedCorpus, Pos, Premise, PremiseSet, remove_marks
+from reprover_b200.dist import shard_bounds
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+# ------------------------------------------------------------------------------- tokenizer mirror
+def test_tokenizer_mirror_matches_golden_probes():
+    for p in json.loads((GOLD / "tokenizer_probes.json").read_text()):
+        assert byt5.encode_ids(p["text"], p["max_length"]) == p["ids"], p
+
+
+def test_needs_id_path_only_for_special_literals():
+    assert not byt5.needs_id_path("theorem foo : a < b ∧ b > c := by simp")
+    assert not byt5.needs_id_path("<a>Nat.add_comm</a> : ∀ n m, n + m = m + n")
+    assert not byt5.needs_id_path("<extra_id_125> is not a token, <extra_id_007> neither")
+    for s in ("x </s>", "<pad>", "a<unk>b", "<extra_id_0>", "<extra_id_124>"):
+        assert byt5.needs_id_path(s)
+
+
+def test_plain_strings_tokenize_as_bytes_plus_three():
+    tok = ref.build_hf_tokenizer()
+    data, offsets = synth.synth_premises(10, seed=3, min_len=1, max_len=50)
+    for s in synth.split_strings(data, offsets):
+        t = s.decode()
+        assert not byt5.needs_id_path(t)
+        assert tok(t).input_ids == [b + 3 for b in s] + [1]
+
+
+def test_pad_batch_layout():
+    ids, mask = byt5.pad_batch([[5, 6, 1], [7, 1]])
+    assert ids.tolist() == [[5, 6, 1], [7, 1, 0]] and mask.tolist() == [[1, 1, 1], [1, 1, 0]]
+
+
+# ------------------------------------------------------------------------------- data model
+def _toy_corpus():
+    def prem(path, name, line, code=None):
+        return Premise(path, name, Pos(line, 0), Pos(line, 10), code or f"theorem {name} : True := trivial")
+
+    a = File("A.lean", [prem("A.lean", "A.one", 1), prem("A.lean", "A.two", 5)])
+    b = File("B.lean", [prem("B.lean", "B.one", 2), prem("B.lean", "B.dup", 4), prem("B.lean", "B.dup", 9)])
+    c = File("C.lean", [prem("C.lean", "C.one", 3), prem("C.lean", "C.two", 7), prem("C.lean", "C.three", 11)])
+    d = File("D.lean", [])
+    return Corpus.from_files([(a, []), (b, ["A.lean"]), (c, ["B.lean"]), (d, [])])
+
+
+def test_pos_ordering_and_context_invariants():
+    assert Pos(1, 5) < Pos(2, 0) and Pos(2, 1) <= Pos(2, 1) and Pos(3, 0) > Pos(2, 9)
+    assert Pos.from_any((4, 2)) == Pos(4, 2)
+    with pytest.raises(AssertionError):
+        Context("A.lean", "thm", Pos(1, 0), "no turnstile here")
+    with pytest.raises(AssertionError):
+        Context("A.lean", "thm", Pos(1, 0), "⊢ <a>x</a>")
+    ctx = Context("A.lean", "thm", (1, 0), "x : Nat\n⊢ x = x")
+    assert ctx.serialize() == "x : Nat\n⊢ x = x" and isinstance(ctx.theorem_pos, Pos)
+    with pytest.raises(AssertionError):
+        Premise("A.lean", "n", Pos(2, 0), Pos(1, 0), "code")
+    with pytest.raises(AssertionError):
+        Premise("A.lean", "n", Pos(1, 0), Pos(1, 0), "")
+
+
+def test_premise_serialize_marks_own_name():
+    p = Premise("M.lean", "Nat.Foo.add_zero", Pos(1, 0), Pos(2, 0), "theorem add_zero (n : Nat) : n + 0 = n := rfl")
+    assert p.serialize() == "theorem <a>Nat.Foo.add_zero</a> (n : Nat) : n + 0 = n := rfl"
+    q = Premise("M.lean", "Nat.bar", Pos(1, 0), Pos(2, 0), "def _root_.Nat.bar := 1")
+    assert q.serialize() == "def <a>Nat.bar</a> := 1"
+    r = Premise("M.lean", "X.y", Pos(1, 0), Pos(2, 0), "instance : Foo := ⟨⟩")
+    assert r.serialize() == "instance : Foo := ⟨⟩"
+    assert remove_marks(p.serialize()) == "theorem Nat.Foo.add_zero (n : Nat) : n + 0 = n := rfl"
+
+
+def test_corpus_accessibility_and_mask():
+    corpus = _toy_corpus()
+    assert len(corpus) == 8 and corpus.num_files == 4 and "C.lean" in corpus
+    assert set(corpus.get_dependencies("C.lean")) == {"A.lean", "B.lean"}
+    assert corpus.file_range("B.lean") == (2, 5)
+    assert corpus.locate_premise("B.lean", Pos(4, 3)).full_name == "B.dup"
+    for path in ("A.lean", "B.lean", "C.lean", "D.lean"):
+        for pos in (Pos(0, 0), Pos(4, 10), Pos(7, 10), Pos(100, 0)):
+            acc = corpus.get_accessible_premises(path, pos)
+            want = np.array([p in acc for p in corpus.all_premises])
+            assert np.array_equal(corpus.accessible_mask(path, pos), want), (path, pos)
+            words = corpus.accessible_mask_words(path, pos)
+            bits = np.unpackbits(words.view(np.uint8), bitorder="little")[: len(corpus)].astype(bool)
+            assert np.array_equal(bits, want)
+    # membership is by (path, full_name): once B.dup@4 is visible, its later duplicate tests True too
+    m = corpus.accessible_mask("B.lean", Pos(5, 0))
+    assert m.tolist() == [True, True, True, True, True, False, False, False]
+    assert corpus.get_accessible_premise_indexes("C.lean", Pos(7, 10)) == [0, 1, 2, 3, 4, 5, 6]
+
+
+def test_corpus_rejects_forward_imports_and_duplicates():
+    a = File("A.lean", [])
+    with pytest.raises(AssertionError):
+        Corpus.from_files([(a, ["Z.lean"])])
+    with pytest.raises(AssertionError):
+        Corpus.from_files([(a, []), (File("A.lean", []), [])])
+
+
+def test_corpus_jsonl_loader_and_filtering(tmp_path):
+    lines = [
+        {"path": "A.lean", "imports": [], "premises": [
+            {"full_name": "A.ok", "code": "theorem ok : True := trivial", "start": [1, 0], "end": [1, 9]},
+            {"full_name": None, "code": "x", "start": [2, 0], "end": [2, 1]},
+            {"full_name": "user__.n.bad", "code": "x", "start": [3, 0], "end": [3, 1]},
+            {"full_name": "[mutual]", "code": "x", "start": [4, 0], "end": [4, 1]},
+            {"full_name": "A.empty", "code": "", "start": [5, 0], "end": [5, 1]}]},
+        {"path": "B.lean", "imports": ["A.lean"], "premises": [
+            {"full_name": "B.x", "code": "def x := 1", "start": [1, 0], "end": [1, 5]}]},
+    ]
+    f = tmp_path / "corpus.jsonl"
+    f.write_text("\n".join(json.dumps(l) for l in lines))
+    corpus = Corpus(str(f))
+    assert [p.full_name for p in corpus.all_premises] == ["A.ok", "B.x"]
+    assert corpus.get_dependencies("B.lean") == ["A.lean"]
+
+
+def test_indexed_corpus_contract_and_pickle(tmp_path):
+    corpus = _toy_corpus()
+    emb = torch.zeros(len(corpus), 8)
+    idx = IndexedCorpus(corpus, emb)
+    with pytest.raises(AssertionError):
+        IndexedCorpus(corpus, torch.zeros(3, 8))
+    path = tmp_path / "index.pickle"
+    path.write_bytes(pickle.dumps(idx))
+    back = pickle.loads(path.read_bytes())
+    assert len(back.corpus) == len(corpus) and back.embeddings.shape == (8, 8)
+    assert back.corpus.accessible_mask("C.lean", Pos(7, 10)).tolist() == corpus.accessible_mask("C.lean", Pos(7, 10)).tolist()
+
+
+def test_premise_set_semantics():
+    s = PremiseSet()
+    p1 = Premise("A.lean", "x", Pos(1, 0), Pos(1, 1), "c")
+    p2 = Premise("A.lean", "x", Pos(9, 0), Pos(9, 1), "other")
+    s.add(p1)
+    assert p2 in s and len(s) == 1
+    s.update([Premise("B.lean", "y", Pos(1, 0), Pos(1, 1), "c")])
+    assert len(s) == 2 and {p.full_name for p in s} == {"x", "y"}
+
+
+# ------------------------------------------------------------------------------- synth / sharding
+def test_synthetic_data_is_deterministic_and_in_spec():
+    d1, o1 = synth.synth_premises(1000, seed=synth.SEED)
+    d2, o2 = synth.synth_premises(1000, seed=synth.SEED)
+    assert np.array_equal(d1, d2) and np.array_equal(o1, o2)
+    lens = np.diff(o1)
+    assert lens.min() >= 16 and lens.max() <= 511 and abs(lens.mean() - 263.5) < 15
+    assert d1.min() >= 0x20 and d1.max() <= 0x7E and (d1 != 0x3C).all()
+    sdat, soff = synth.synth_states(5)
+    for s in synth.split_strings(sdat, soff):
+        assert s.decode().startswith("⊢ ")
+    sd = synth.random_t5_state_dict(synth.tiny_config(1), seed=1)
+    sd2 = synth.random_t5_state_dict(synth.tiny_config(1), seed=1)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert sd["encoder.block.0.layer.0.SelfAttention.q.weight"].shape == (384, 1472)
+
+
+def test_shard_bounds_partition_rows():
+    for n, w in ((10, 3), (1_600_000, 8), (5, 8), (0, 2)):
+        b = shard_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        sizes = np.diff(b)
+        assert (sizes >= 0).all() and sizes.max() - sizes.min() <= 1

@@ -1,0 +1,134 @@
+"""Pins the oracle (test infrastructure) against the real third-party code the reference calls
+(HF transformers + torch, installed here and on the GPU box) and against the committed golden
+fixtures.  CPU only."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import reference_path as ref
+from reprover_b200 import synth
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_c_bucket_function_matches_hf_and_golden():
+    from transformers.models.t5.modeling_t5 import T5Attention
+
+    rel = torch.arange(-300, 301)
+    want = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128).tolist()
+    got = [c_oracle.relative_bucket(int(r)) for r in rel]
+    assert got == want
+    g = json.loads((GOLD / "bucket_table.json").read_text())
+    assert [c_oracle.relative_bucket(r) for r in g["relative_position"]] == g["bucket"]
+
+
+def test_c_tokenizer_matches_hf():
+    tok = ref.build_hf_tokenizer()
+    data, offsets = synth.synth_premises(40, seed=7, min_len=1, max_len=80)
+    texts = [s.decode() for s in synth.split_strings(data, offsets)]
+    for max_len in (512, 33, 8, 2, 1):
+        ids, cu = c_oracle.tokenize(data, offsets, max_len)
+        for i, t in enumerate(texts):
+            want = tok(t, max_length=max_len, truncation=True).input_ids
+            assert ids[cu[i]:cu[i + 1]].tolist() == want, (i, max_len)
+    # multi-byte UTF-8 (truncation may cut a code point: ids are bytes, so that is fine)
+    s = "⊢ ∀ x : ℝ, x ≤ |x| ∧ «é»"
+    b = np.frombuffer(s.encode(), dtype=np.uint8)
+    for max_len in (512, 7):
+        ids, cu = c_oracle.tokenize(b, np.array([0, len(b)]), max_len)
+        assert ids.tolist() == tok(s, max_length=max_len, truncation=True).input_ids
+
+
+def test_golden_tokenizer_probes_still_match_hf():
+    tok = ref.build_hf_tokenizer()
+    for p in json.loads((GOLD / "tokenizer_probes.json").read_text()):
+        assert tok(p["text"], max_length=p["max_length"], truncation=True).input_ids == p["ids"]
+
+
+def test_dot64_is_exact_sum_of_exact_products():
+    rng = np.random.default_rng(0)
+    for d in (64, 1472, 4096):
+        q = torch.from_numpy(rng.standard_normal(d).astype(np.float32)).to(torch.bfloat16)
+        e = torch.from_numpy(rng.standard_normal(d).astype(np.float32)).to(torch.bfloat16)
+        got = c_oracle.dot64(c_oracle.bf16_bits(q), c_oracle.bf16_bits(e))
+        import math
+
+        exact = math.fsum((q.double() * e.double()).tolist())  # products are exact in fp64
+        assert abs(got - exact) <= 1e-13 * max(1.0, abs(exact))
+    # order sensitivity is below the tie-break resolution but the value is deterministic
+    assert c_oracle.dot64(c_oracle.bf16_bits(q), c_oracle.bf16_bits(e)) == got
+
+
+def test_c_topk_matches_numpy_bruteforce():
+    rng = np.random.default_rng(1)
+    nq, n, d, k = 7, 600, 192, 20
+    Q = torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)).to(torch.bfloat16)
+    E = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).to(torch.bfloat16)
+    E[100:110] = E[5]  # exact duplicates -> ties broken by index
+    mask = rng.random((nq, n)) < 0.7
+    mask[0] = False
+    mask[1, :] = False
+    mask[1, [3, 4]] = True
+    words = np.zeros((nq, (n + 31) // 32 * 32), dtype=bool)
+    words[:, :n] = mask
+    words = np.packbits(words.reshape(nq, -1, 8), axis=2, bitorder="little").reshape(nq, -1).view("<u4").copy()
+    s, i, c = c_oracle.sim_topk(c_oracle.bf16_bits(Q), c_oracle.bf16_bits(E), k, words)
+    S = np.array([[c_oracle.dot64(c_oracle.bf16_bits(Q[a]), c_oracle.bf16_bits(E[b])) for b in range(n)] for a in range(nq)])
+    S = np.where(mask, S, -np.inf)
+    order = np.argsort(-S, axis=1, kind="stable")[:, :k]
+    for a in range(nq):
+        m = int(min(k, mask[a].sum()))
+        assert c[a] == m
+        assert i[a, :m].tolist() == order[a, :m].tolist()
+        assert (i[a, m:] == -1).all() and np.isneginf(s[a, m:]).all()
+        assert np.array_equal(s[a, :m], S[a, order[a, :m]])
+    # the plain-python restatement of get_nearest_premises ranks the same way
+    o2, s2 = ref.topk_plain(Q[2:], E, k, mask[2:])
+    np.testing.assert_allclose(s2, s[2:], rtol=0, atol=1e-12)
+
+
+def test_c_merge_equals_topk_of_concatenation():
+    rng = np.random.default_rng(2)
+    nq, d, k = 5, 128, 10
+    Q = torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)).to(torch.bfloat16)
+    shards = [torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).to(torch.bfloat16) for n in (50, 7, 120)]
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in shards])])
+    parts = [c_oracle.sim_topk(c_oracle.bf16_bits(Q), c_oracle.bf16_bits(x), k, None, int(offs[r])) for r, x in enumerate(shards)]
+    ms, mi, mc = c_oracle.topk_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    ws, wi, wc = c_oracle.sim_topk(c_oracle.bf16_bits(Q), c_oracle.bf16_bits(torch.cat(shards)), k)
+    assert np.array_equal(mi, wi) and np.array_equal(ms, ws) and np.array_equal(mc, wc)
+
+
+def test_golden_cfg1_embeddings_reproduce():
+    """BASELINE config 1 (8 premises + 1 state, ByT5-small geometry, CPU, cosine top-3): the oracle on
+    the installed HF/torch reproduces the committed fixture (guards against version drift of the
+    third-party arithmetic and of the synthetic checkpoint generator)."""
+    g = np.load(GOLD / "cfg1.npz")
+    cfg = dict(synth.BYT5_SMALL)
+    sd = synth.random_t5_state_dict(cfg, seed=int(g["weight_seed"]))
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["weight_checksum"])) < 1e-6
+    data, offsets = synth.synth_premises(8, seed=synth.SEED)
+    assert np.array_equal(data, g["data"][: len(data)])
+    torch.set_float32_matmul_precision("highest")
+    texts = [s.decode() for s in synth.split_strings(g["data"], g["offsets"])]
+    emb = ref.reindex_corpus(ref.build_hf_encoder(cfg, sd), ref.build_hf_tokenizer(), texts, 64, 512).numpy()
+    np.testing.assert_allclose(emb, g["embeddings"], rtol=0, atol=2e-5)
+    sims = emb[8:] @ emb[:8].T
+    assert np.argsort(-sims, axis=1, kind="stable")[:, :3].tolist() == g["top3"].tolist()
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+def test_oracle_encode_is_padding_invariant():
+    """Packed var-len execution is legitimate: padded keys get zero weight."""
+    cfg = synth.tiny_config(1)
+    sd = synth.random_t5_state_dict(cfg, seed=4)
+    enc, tok = ref.build_hf_encoder(cfg, sd), ref.build_hf_tokenizer()
+    data, offsets = synth.synth_premises(5, seed=4, min_len=2, max_len=60)
+    texts = [s.decode() for s in synth.split_strings(data, offsets)]
+    a = ref.reindex_corpus(enc, tok, texts, 5, 64)
+    b = ref.reindex_corpus(enc, tok, texts, 1, 64)
+    assert torch.allclose(a, b, atol=1e-6)

@@ -1,0 +1,156 @@
+"""The drop-in surface end to end on a B200: `B200PremiseRetriever` (load_hf / load_corpus /
+reindex_corpus / retrieve) and `Corpus.get_nearest_premises` against the oracle restatement of
+the reference path (oracle/reference_path.py) on the same synthetic checkpoint and corpus."""
+import json
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from reprover_b200 import synth
+from reprover_b200.corpus import Context, Corpus, File, Pos, Premise
+from reprover_b200.retriever import B200PremiseRetriever
+from tests.helpers import EMB_MAX_ABS, EMB_MIN_COS, compare_embeddings, ref
+
+pytestmark = pytest.mark.gpu
+MAX_LEN = 192
+
+
+def _make_corpus(n_files=4, per_file=45, seed=0):
+    rng = np.random.default_rng(seed)
+    files, all_lines = [], []
+    for f in range(n_files):
+        path = f"Synth/F{f}.lean"
+        prem = []
+        for j in range(per_file):
+            n = int(rng.integers(10, 160))
+            body = bytes(rng.choice(synth._ALPHABET, size=n).tolist()).decode()
+            name = f"Synth.F{f}.lemma_{j}"
+            code = f"theorem lemma_{j} : {body}"
+            if f == 1 and j == 3:
+                code += " <pad> sentinel </s> tail <extra_id_5>"   # forces the host-tokenised ids path
+            prem.append({"full_name": name, "code": code, "start": [10 * j + 1, 0], "end": [10 * j + 5, 0]})
+        imports = [f"Synth/F{i}.lean" for i in range(f) if (f - i) <= 2]   # F2 imports F0,F1; F3 imports F1,F2 (+F0 transitively)
+        all_lines.append({"path": path, "imports": imports, "premises": prem})
+    return all_lines
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory, cuda_device):
+    tmp = tmp_path_factory.mktemp("retr")
+    cfg = synth.tiny_config(num_layers=2)
+    sd = synth.random_t5_state_dict(cfg, seed=21)
+    ckpt = tmp / "ckpt"
+    synth.save_hf_checkpoint(str(ckpt), cfg, sd)
+    jsonl = tmp / "corpus.jsonl"
+    jsonl.write_text("\n".join(json.dumps(l) for l in _make_corpus()))
+    retr = B200PremiseRetriever.load_hf(str(ckpt), MAX_LEN, cuda_device)
+    retr.load_corpus(str(jsonl))
+    assert retr.embeddings_staled and retr.corpus_embeddings is None
+    retr.reindex_corpus(batch_size=32)
+    torch.set_float32_matmul_precision("highest")
+    enc, tok = ref.build_hf_encoder(cfg, sd), ref.build_hf_tokenizer()
+    return dict(tmp=tmp, cfg=cfg, sd=sd, ckpt=ckpt, jsonl=jsonl, retr=retr, enc=enc, tok=tok)
+
+
+def test_load_hf_surface(setup):
+    r = setup["retr"]
+    assert r.embedding_size == 1472 and r.max_seq_len == MAX_LEN and r.num_retrieved == 100
+    assert r.dtype == torch.bfloat16                      # reference policy on cc >= 8 (model.py:59-64)
+    assert not r.embeddings_staled and r.corpus_embeddings.shape == (len(r.corpus), 1472)
+    assert r.corpus_embeddings.device.type == "cuda" and r.corpus_embeddings.dtype == torch.bfloat16
+
+
+def test_reindex_matches_oracle(setup):
+    r = setup["retr"]
+    texts = [p.serialize() for p in r.corpus.all_premises]
+    want = ref.reindex_corpus(setup["enc"], setup["tok"], texts, 32, MAX_LEN)
+    max_abs, min_cos = compare_embeddings(r.corpus_embeddings, want)
+    assert max_abs <= EMB_MAX_ABS + 2e-3 and min_cos >= EMB_MIN_COS, (max_abs, min_cos)   # + bf16 output rounding
+    # reindex is a no-op while the index is fresh (reference :185-186)
+    before = r.corpus_embeddings
+    r.reindex_corpus(batch_size=7)
+    assert r.corpus_embeddings is before
+
+
+def test_retrieve_matches_reference_walk(setup):
+    """Top-k accessible premises, best first: the engine's ranking equals the oracle's
+    `get_nearest_premises` run on the engine's own embedding matrix (SURVEY §7 parity definition)."""
+    r = setup["retr"]
+    corpus = r.corpus
+    sdat, soff = synth.synth_states(6, seed=77, min_len=12, max_len=150)
+    states = [s.decode() for s in synth.split_strings(sdat, soff)]
+    cases = [("Synth/F3.lean", Pos(200, 0)), ("Synth/F2.lean", Pos(31, 0)), ("Synth/F1.lean", Pos(446, 0)),
+             ("Synth/F3.lean", Pos(1, 0)), ("Synth/F0.lean", Pos(446, 0)), ("Synth/F2.lean", Pos(9999, 0))]
+    k = 10
+    for state, (path, pos) in zip(states, cases):
+        premises, scores = r.retrieve(state, path, "Synth.thm", pos, k)
+        assert len(premises) == len(scores) == k
+        ctx = Context(path, "Synth.thm", pos, state)
+        ctx_emb = r.encode_texts([state])
+        want_p, want_s = ref.get_nearest_premises(corpus, r.corpus_embeddings.cpu(), [ctx], ctx_emb.cpu(), k)
+        assert [p.full_name for p in premises] == [p.full_name for p in want_p[0]]
+        assert np.allclose(scores, want_s[0], atol=1e-6)
+        acc = corpus.get_accessible_premises(path, pos)
+        assert all(p in acc for p in premises)
+        assert all(scores[i] >= scores[i + 1] for i in range(k - 1))
+    # the context embedding itself agrees with the oracle encoder
+    tok = ref.tokenize(setup["tok"], states, MAX_LEN)
+    want = ref.encode(setup["enc"], tok.input_ids, tok.attention_mask)
+    max_abs, min_cos = compare_embeddings(r.encode_texts(states), want)
+    assert max_abs <= EMB_MAX_ABS + 2e-3 and min_cos >= EMB_MIN_COS
+
+
+def test_retrieve_raises_when_too_few_accessible(setup):
+    r = setup["retr"]
+    with pytest.raises(ValueError):        # reference common.py:323-324
+        r.retrieve("⊢ True", "Synth/F0.lean", "Synth.thm", Pos(26, 0), 10)   # only 3 premises end before line 26
+    got, _ = r.retrieve("⊢ True", "Synth/F0.lean", "Synth.thm", Pos(26, 0), 3)
+    assert sorted(p.full_name for p in got) == ["Synth.F0.lemma_0", "Synth.F0.lemma_1", "Synth.F0.lemma_2"]
+
+
+def test_batched_retrieve_equals_single(setup):
+    r = setup["retr"]
+    sdat, soff = synth.synth_states(5, seed=78, min_len=12, max_len=100)
+    states = [s.decode() for s in synth.split_strings(sdat, soff)]
+    P, S = r.retrieve_batch(states, ["Synth/F3.lean"] * 5, ["t"] * 5, [Pos(300, 0)] * 5, 20)
+    for i, st in enumerate(states):
+        p1, s1 = r.retrieve(st, "Synth/F3.lean", "t", Pos(300, 0), 20)
+        assert [p.full_name for p in p1] == [p.full_name for p in P[i]] and s1 == S[i]
+
+
+def test_encode_signature_parity(setup):
+    r = setup["retr"]
+    texts = ["⊢ a = b", "x y z : Nat\n⊢ x + (y + z) = x + y + z"]
+    tok = ref.tokenize(setup["tok"], texts, MAX_LEN)
+    got = r._encode(tok.input_ids.to(r.device), tok.attention_mask.to(r.device))
+    want = ref.encode(setup["enc"], tok.input_ids, tok.attention_mask)
+    max_abs, min_cos = compare_embeddings(got, want)
+    assert got.dtype == torch.bfloat16 and max_abs <= EMB_MAX_ABS + 2e-3 and min_cos >= EMB_MIN_COS
+
+
+def test_index_roundtrip_and_cli(setup, tmp_path, cuda_device):
+    from reprover_b200 import index_cli
+
+    out = tmp_path / "index.pickle"
+    index_cli.main(["--ckpt_path", str(setup["ckpt"]), "--corpus-path", str(setup["jsonl"]),
+                    "--output-path", str(out), "--batch-size", "16", "--max-seq-len", str(MAX_LEN)])
+    indexed = pickle.loads(out.read_bytes())
+    assert indexed.embeddings.dtype == torch.float32 and indexed.embeddings.device.type == "cpu"
+    assert torch.equal(indexed.embeddings, setup["retr"].corpus_embeddings.float().cpu())
+    r2 = B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device)
+    r2.load_corpus(str(out))                                # pickled IndexedCorpus -> fresh index (model.py:81-85)
+    assert not r2.embeddings_staled
+    a = r2.retrieve("⊢ p ∧ q", "Synth/F3.lean", "t", Pos(120, 0), 7)
+    b = setup["retr"].retrieve("⊢ p ∧ q", "Synth/F3.lean", "t", Pos(120, 0), 7)
+    assert [p.full_name for p in a[0]] == [p.full_name for p in b[0]] and a[1] == b[1]
+    assert r2.corpus_embeddings.device.type == "cuda" and r2.corpus_embeddings.dtype == torch.bfloat16
+
+
+def test_fp32_embedding_dtype_option(setup, cuda_device):
+    r = B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=torch.float32)
+    e = r.encode_texts(["⊢ x = x"])
+    assert e.dtype == torch.float32 and abs(float(e.norm()) - 1.0) < 1e-5
+    with pytest.raises(NotImplementedError):
+        B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=torch.float16)
