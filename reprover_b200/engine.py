@@ -69,6 +69,9 @@ class T5EncoderEngine:
         self._ws: Optional[torch.Tensor] = None
         self._ws_shape = (0, 0)
         self._debug_buf: Optional[torch.Tensor] = None
+        self._pin_bufs: List[Optional[torch.Tensor]] = [None, None]
+        self._pin_events: List[Optional[torch.cuda.Event]] = [None, None]
+        self._pin_slot = 0
         with torch.cuda.device(self.device):
             _native.check(self.lib.rpx_device_check())
             cfg = _native.T5Config(
@@ -170,9 +173,7 @@ class T5EncoderEngine:
         counts = self.token_counts(offsets, max_seq_len)
         cum = np.concatenate([[0], np.cumsum(counts)])
         lo = 0
-        data_t = torch.from_numpy(np.ascontiguousarray(data))
-        if not data_t.is_pinned():
-            data_t = data_t.pin_memory()
+        data_t = self._pinned_copy(data)
         while lo < n:
             hi = int(np.searchsorted(cum, cum[lo] + self.max_tokens_per_call, side="right")) - 1
             hi = max(hi, lo + 1)
@@ -182,7 +183,23 @@ class T5EncoderEngine:
                 1, dtype=torch.uint8, device=self.device)
             self.encode_packed_bytes(d_bytes, offsets[lo:hi + 1] - b0, max_seq_len, out[lo:hi])
             lo = hi
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pin_events[self._pin_slot] = ev
         return out
+
+    def _pinned_copy(self, data: np.ndarray) -> torch.Tensor:
+        """Copy host bytes into a reusable page-locked staging buffer (H2D from it is asynchronous).
+        Two buffers alternate; a buffer is refilled only after the copies that read it have finished."""
+        n = int(data.size)
+        self._pin_slot ^= 1
+        slot = self._pin_slot
+        if self._pin_bufs[slot] is None or self._pin_bufs[slot].numel() < n:
+            self._pin_bufs[slot] = torch.empty(max(n, 1 << 20), dtype=torch.uint8).pin_memory()
+        elif self._pin_events[slot] is not None:
+            self._pin_events[slot].synchronize()
+        self._pin_bufs[slot][:n].numpy()[...] = np.asarray(data, dtype=np.uint8).reshape(-1)
+        return self._pin_bufs[slot][:n]
 
     def encode_strings(self, texts: Sequence[bytes], max_seq_len: int, **kw) -> torch.Tensor:
         lens = np.fromiter((len(t) for t in texts), dtype=np.int64, count=len(texts))

@@ -88,23 +88,33 @@ class B200PremiseRetriever:
         return self.encoder.encode_ids(input_ids, attention_mask, out_dtype=self.dtype)
 
     @torch.no_grad()
-    def encode_texts(self, texts: Sequence[str], batch_size: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def encode_texts(self, texts: Sequence[str], batch_size: int = 64, out: Optional[torch.Tensor] = None,
+                     host_chunk: int = 1024) -> torch.Tensor:
         """tokenizer(...) + `_encode` for a list of strings (reference :199-206), rows in input order.
 
         Strings without special-token literals (practically all Lean code) go to the device as raw
-        bytes; the rest are tokenised on the host with HF semantics and use the ids entry point."""
+        bytes; the rest are tokenised on the host with HF semantics and use the ids entry point.
+        Work is issued in chunks of `host_chunk` strings: engine calls are asynchronous, so the host
+        prepares chunk i+1 while the GPU encodes chunk i."""
         n = len(texts)
         if out is None:
             out = torch.empty(n, self.embedding_size, dtype=self.dtype, device=self.device)
-        plain = [i for i, t in enumerate(texts) if not byt5.needs_id_path(t)]
-        special = [i for i, t in enumerate(texts) if byt5.needs_id_path(t)]
-        if plain:
-            blobs = [texts[i].encode("utf-8") for i in plain]
-            if len(plain) == n:
-                self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype, out=out)
-            else:
-                emb = self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype)
-                out[torch.tensor(plain, device=self.device)] = emb
+        special: List[int] = []
+        for lo in range(0, n, host_chunk):
+            hi = min(n, lo + host_chunk)
+            chunk = texts[lo:hi]
+            odd = [i for i, t in enumerate(chunk) if "<" in t and byt5.needs_id_path(t)]
+            if not odd:
+                self.encoder.encode_strings([t.encode("utf-8") for t in chunk], self.max_seq_len,
+                                            out_dtype=self.dtype, out=out[lo:hi])
+                continue
+            special.extend(lo + i for i in odd)
+            odd_set = set(odd)
+            plain = [i for i in range(hi - lo) if i not in odd_set]
+            if plain:
+                emb = self.encoder.encode_strings([chunk[i].encode("utf-8") for i in plain], self.max_seq_len,
+                                                  out_dtype=self.dtype)
+                out[torch.tensor([lo + i for i in plain], device=self.device)] = emb
         for lo in range(0, len(special), batch_size):
             rows = special[lo:lo + batch_size]
             ids, mask = byt5.pad_batch([byt5.encode_ids(texts[i], self.max_seq_len) for i in rows])
@@ -119,10 +129,14 @@ class B200PremiseRetriever:
         if not self.embeddings_staled:
             return
         assert self.corpus is not None, "load_corpus first"
-        texts = [p.serialize() for p in self.corpus.all_premises]
-        self.corpus_embeddings = torch.zeros(len(texts), self.embedding_size, dtype=self.dtype, device=self.device)
-        if texts:
-            self.encode_texts(texts, batch_size=batch_size, out=self.corpus_embeddings)
+        premises = self.corpus.all_premises
+        self.corpus_embeddings = torch.zeros(len(premises), self.embedding_size, dtype=self.dtype, device=self.device)
+        # serialise lazily, a chunk at a time, so the regex work overlaps the GPU (see encode_texts)
+        chunk = 1024
+        for lo in range(0, len(premises), chunk):
+            hi = min(len(premises), lo + chunk)
+            self.encode_texts([p.serialize() for p in premises[lo:hi]], batch_size=batch_size,
+                              out=self.corpus_embeddings[lo:hi])
         self.embeddings_staled = False
 
     # ------------------------------------------------------------------ retrieve (reference :338-375)
