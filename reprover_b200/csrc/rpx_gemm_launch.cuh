@@ -37,7 +37,7 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
   int grid = tiles_m * tiles_n;
   int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
   if (grid > cap) grid = cap;
-  kern<<<grid, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, ep);
+  kern<<<grid, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, 1, ep);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }

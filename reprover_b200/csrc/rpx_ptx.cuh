@@ -51,8 +51,23 @@ RPX_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 RPX_DEVICE void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef RPX_WAIT_HINT_NS
+#define RPX_WAIT_HINT_NS 2000
+#endif
 RPX_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if RPX_WAIT_HINT_NS > 0
+  // suspend-time hint: the thread may sleep in hardware up to this long before re-polling
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)RPX_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -62,6 +77,7 @@ RPX_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok;
 }
 // Bounded wait.  `tag` identifies the call site in the trap message.  try_wait suspends the

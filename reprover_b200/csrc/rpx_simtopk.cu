@@ -45,6 +45,11 @@ struct EpiSimTopk {
     uint2* cand;           // [grid][128][CAP]  (score bits, local index)
     int32_t* cnt;          // [grid][128]
     uint32_t* gthr;        // [tiles_m*128] shared per-query threshold (monotone key, atomicMax)
+    uint32_t* gmin;        // [tiles_m*128] min over CTAs of their first published rank_r-th best key
+    uint32_t* gcnt;        // [tiles_m*128] number of CTAs that have published into gmin
+    int n_seg;             // CTAs per query block
+    int rank_r;            // ceil(KEEP / n_seg)
+    int final_max;         // longest list stage 2 accepts (CAP: no final compaction; else KEEP+SLACK)
     const uint32_t* mask;  // optional access bitmask [nq][mask_stride]
     int64_t mask_stride;
     int nq;
@@ -61,12 +66,18 @@ struct EpiSimTopk {
   uint2* warp_buf;  // list of lane 0's query; lane l's list is warp_buf + l*CAP
   int q, lane, slot;
   bool active;
+  bool published = false;  // this list has contributed to gmin
+  bool have_gmin = false;  // the all-CTA bound has been adopted
 
   __device__ EpiSimTopk(const Params& p_, uint8_t*, int row, int) : p(p_) {
     lane = row & 31;
     q = (blockIdx.x % p.tiles_m) * kBlockM + row;
     active = q < p.nq;
+#ifdef RPX_SIM_NOAPPEND  // tuning experiment: mainloop + TMEM read + compare floor (results are wrong)
+    thr = INFINITY;
+#else
     thr = -INFINITY;
+#endif
     warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + (row & ~31)) * CAP;
     buf = warp_buf + (size_t)lane * CAP;
     wptr = buf;
@@ -103,50 +114,83 @@ struct EpiSimTopk {
         : "memory");
   }
 
+  // Loads lane-strided entries [i*32 + lane] of list `b` (count c) into registers.
+  __device__ __forceinline__ void load_list(const uint2* b, int c, uint2 (&e)[EPL]) const {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int pos = i * 32 + lane;
+      e[i] = pos < c ? b[pos] : make_uint2(0u, 0u);
+    }
+  }
+
+  // Largest T with count(key >= T) >= target, by bisection on [lo, hi) with
+  // count(>= lo) >= target > count(>= hi).  Returns T and the count at T.
+  __device__ __forceinline__ uint32_t kth_key(const uint32_t (&key)[EPL], int c, int target, int slack,
+                                              uint64_t lo, uint64_t hi, int count_lo, int* count_out) const {
+    while (count_lo > target + slack && hi - lo > 1) {
+      const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
+      int m = 0;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) m += (i * 32 + lane < c && key[i] >= mid) ? 1 : 0;
+      m = __reduce_add_sync(kFull, m);
+      if (m >= target) {
+        lo = mid;
+        count_lo = m;
+      } else {
+        hi = mid;
+      }
+    }
+    *count_out = count_lo;
+    return (uint32_t)lo;
+  }
+
   // Warp-cooperative compaction of every list in this warp that holds more than `min_count`
   // entries: a bisection over the monotone score keys finds a threshold that keeps between KEEP
-  // and KEEP+SLACK entries (exactly KEEP, lowest indices first, when many scores tie).
+  // and KEEP+SLACK entries (exactly KEEP, lowest indices first, when many scores tie).  The next
+  // list's entries are fetched while the current one is processed.
   __device__ void compact_warp(int min_count) {
     const int my_cnt = count();
-    for (int src = 0; src < 32; ++src) {
-      const int c = __shfl_sync(kFull, my_cnt, src);
-      if (c <= min_count) continue;  // warp-uniform
+    unsigned todo = __ballot_sync(kFull, my_cnt > min_count);
+    if (todo == 0u) return;
+    uint2 e[EPL], en[EPL];
+    int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int c = __shfl_sync(kFull, my_cnt, src);
+    load_list(warp_buf + (size_t)src * CAP, c, e);
+    while (src >= 0) {
+      const int nsrc = todo ? __ffs(todo) - 1 : -1;
+      todo &= todo - 1;
+      int cn = 0;
+      if (nsrc >= 0) {
+        cn = __shfl_sync(kFull, my_cnt, nsrc);
+        load_list(warp_buf + (size_t)nsrc * CAP, cn, en);
+      }
       uint2* b = warp_buf + (size_t)src * CAP;
-      uint2 e[EPL];
       uint32_t key[EPL];
       uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        const int pos = i * 32 + lane;
-        if (pos < c) {
-          e[i] = b[pos];
+        if (i * 32 + lane < c) {
           key[i] = fkey(e[i].x);
           kmin = min(kmin, key[i]);
           kmax = max(kmax, key[i]);
         } else {
-          e[i] = make_uint2(0u, 0u);
           key[i] = 0u;
         }
       }
       kmin = __reduce_min_sync(kFull, kmin);
       kmax = __reduce_max_sync(kFull, kmax);
       // invariant: count(key >= lo) = count_lo >= KEEP ; count(key >= hi) < KEEP
-      uint64_t lo = kmin, hi = (uint64_t)kmax + 1;
-      int count_lo = c;
-      while (count_lo > KEEP + SLACK && hi - lo > 1) {
-        const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
-        int m = 0;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) m += (i * 32 + lane < c && key[i] >= mid) ? 1 : 0;
-        m = __reduce_add_sync(kFull, m);
-        if (m >= KEEP) {
-          lo = mid;
-          count_lo = m;
-        } else {
-          hi = mid;
-        }
+      int count_lo;
+      const uint32_t lo32 = kth_key(key, c, KEEP, SLACK, kmin, (uint64_t)kmax + 1, c, &count_lo);
+      // one-time global bound: the R-th best of this list (R = ceil(KEEP / #CTAs of the block)); once
+      // every CTA of the query block has published one, >= KEEP entries exceed their minimum.
+      const bool publish = __shfl_sync(kFull, (int)!published, src) != 0;
+      uint32_t rth = 0u;
+      if (publish) {
+        int dummy;
+        rth = kth_key(key, c, p.rank_r, 0, lo32, (uint64_t)kmax + 1, count_lo, &dummy);
       }
-      const uint32_t lo32 = (uint32_t)lo;
       const bool tie_mode = count_lo > KEEP + SLACK;  // > SLACK entries share the key `lo`
       int need_eq = 0;
       if (tie_mode) {
@@ -184,7 +228,17 @@ struct EpiSimTopk {
         // This CTA holds >= KEEP entries with key >= lo, so no entry with key < lo can be in the
         // query's global top-KEEP: publish the bound for the other CTAs serving this query block.
         atomicMax(p.gthr + q, lo32 - 1u);
+        if (publish) {
+          atomicMin(p.gmin + q, rth);
+          __threadfence();
+          atomicAdd(p.gcnt + q, 1u);
+          published = true;
+        }
       }
+      src = nsrc;
+      c = cn;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) e[i] = en[i];
     }
     __syncwarp();
   }
@@ -193,11 +247,19 @@ struct EpiSimTopk {
   __device__ void tile(const TileCtx& t) {
     // adopt the best bound any CTA of this query block has published so far
     if (active) {
-      const uint32_t g = __ldcg(p.gthr + q);
+      uint32_t g = __ldcg(p.gthr + q);
+      if (!have_gmin && __ldcg(p.gcnt + q) >= (uint32_t)p.n_seg) {
+        __threadfence();
+        const uint32_t gm = __ldcg(p.gmin + q);  // every CTA holds >= rank_r entries with key >= gm
+        g = max(g, gm - 1u);
+        have_gmin = true;
+      }
       if (g > fkey(__float_as_uint(thr))) thr = __uint_as_float(unkey(g));
     }
     for (int c = 0; c < t.n_cols; c += 32) {
-      if (__any_sync(kFull, count() > CAP - 32)) compact_warp(KEEP);
+      // only the lists that are actually about to overflow are compacted: after the warm-up (when
+      // all 32 fill together) that is typically a single lane, so the other warps are not held up
+      if (__any_sync(kFull, count() > CAP - 32)) compact_warp(CAP - 64);
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
       tmem_ld_wait();
@@ -217,11 +279,104 @@ struct EpiSimTopk {
   }
 
   __device__ void finish() {
-    // hand stage 2 short lists
-    if (__any_sync(kFull, count() > KEEP + SLACK)) compact_warp(KEEP + SLACK);
+    // stage 2 keeps all lists of a query in shared memory: shorten them only if they would not fit
+    if (p.final_max < CAP && __any_sync(kFull, count() > p.final_max)) compact_warp(p.final_max);
     p.cnt[slot] = count();
   }
 };
+
+// ------------------------------------------------------------------------------------ stage 0
+// Sampling pass: scores of every query against a strided sample of corpus tiles (n_blk_stride > 1)
+// are written out ([rows][ld] fp32, -inf where masked / out of range); sample_threshold_kernel
+// then takes, per query, the n_res-th best sample score as the starting threshold of stage 1.
+// With ~8k sampled premises the main pass admits ~1.4 % of the scores, so its lists hardly ever
+// need compacting.  (A threshold from a sample is always valid: at least n_res premises — the
+// sampled ones — score at or above it.)
+struct EpiSampleScores {
+  struct Params {
+    float* S;
+    int ld;
+    const uint32_t* mask;
+    int64_t mask_stride;
+    int nq;
+    int n;
+  };
+  static constexpr size_t kSmemBytes = 0;
+  static constexpr int kWarps = 4;
+  Params p;
+  __device__ EpiSampleScores(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ void before_wait(const TileCtx&) {}
+  __device__ void tile(const TileCtx& t) {
+    const int q = t.m0 + t.row;
+    const bool active = q < p.nq;
+    float* dst = p.S + (size_t)q * p.ld + (size_t)t.n_blk * kSimBlockN;
+    for (int c = 0; c < kSimBlockN; c += 32) {
+      uint32_t v[32];
+      if (c < t.n_cols) {
+        tmem_ld_32x32(t.tmem + c, v);
+        tmem_ld_wait();
+      }
+      const int base = t.n0 + c;
+      uint32_t word = 0u;
+      if (c < t.n_cols) {
+        word = 0xFFFFFFFFu;
+        if (p.mask != nullptr && active) word = p.mask[(size_t)q * p.mask_stride + (base >> 5)];
+        if (base + 32 > p.n) word &= (1u << (p.n - base)) - 1u;
+      }
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = ((word >> (j + 0)) & 1u) ? __uint_as_float(v[j + 0]) : -INFINITY;
+          o.y = ((word >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : -INFINITY;
+          o.z = ((word >> (j + 2)) & 1u) ? __uint_as_float(v[j + 2]) : -INFINITY;
+          o.w = ((word >> (j + 3)) & 1u) ? __uint_as_float(v[j + 3]) : -INFINITY;
+          *reinterpret_cast<float4*>(dst + c + j) = o;
+        }
+      }
+    }
+  }
+  __device__ void finish() {}
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity);
+
+// One CTA per query: gthr[q] = (n_res-th largest sample key) - 1, or 0 when fewer than n_res
+// sampled premises are admissible.
+__global__ void __launch_bounds__(256)
+sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_res, uint32_t* __restrict__ gthr) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  uint32_t* keys = reinterpret_cast<uint32_t*>(sm_raw);
+  __shared__ int redi[32];
+  __shared__ uint32_t redu[32];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t kNegInf = fkey(0xFF800000u);
+  uint32_t kmax = 0u;
+  int valid = 0;
+  for (int i = tid; i < n_cols; i += 256) {
+    const uint32_t k = fkey(__float_as_uint(S[(size_t)q * ld + i]));
+    keys[i] = k;
+    kmax = max(kmax, k);
+    valid += k > kNegInf ? 1 : 0;
+  }
+  valid = block_reduce<int>(valid, redi, [](int a, int b) { return a + b; }, 0);
+  kmax = block_reduce<uint32_t>(kmax, redu, [](uint32_t a, uint32_t b) { return a > b ? a : b; }, 0u);
+  if (valid < n_res) {
+    if (tid == 0) gthr[q] = 0u;
+    return;
+  }
+  // largest T with count(key >= T) >= n_res
+  uint64_t lo = (uint64_t)kNegInf + 1, hi = (uint64_t)kmax + 1;  // count(>= lo) = valid >= n_res; count(>= hi) = 0
+  while (hi - lo > 1) {
+    const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
+    int m = 0;
+    for (int i = tid; i < n_cols; i += 256) m += keys[i] >= mid ? 1 : 0;
+    m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
+    if (m >= n_res) lo = mid; else hi = mid;
+  }
+  if (tid == 0) gthr[q] = (uint32_t)lo - 1u;
+}
 
 // ------------------------------------------------------------------------------------ stage 2
 
@@ -234,17 +389,45 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
                                                   const __nv_bfloat16* __restrict__ erow, int d, int lane) {
   double acc = 0.0;
   const int chunks = d >> 3;
-  for (int ch = lane; ch < chunks; ch += 32) {
-    const uint4 ev = *reinterpret_cast<const uint4*>(erow + ch * 8);
-    const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
-    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
-    const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+  // all of this lane's 16-byte loads of the (cold, DRAM-resident) index row go out before the first
+  // dependent fma; the summation order is unchanged
+  constexpr int kMaxIter = 8;  // d <= 8 * 32 * 8 = 2048 takes the batched path
+  if (chunks <= kMaxIter * 32) {
+    uint4 ev[kMaxIter];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
-      const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
-      acc = fma(q0, e0, acc);
-      acc = fma(q1, e1, acc);
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int ch = lane + it * 32;
+      ev[it] = ch < chunks ? *reinterpret_cast<const uint4*>(erow + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int ch = lane + it * 32;
+      if (ch < chunks) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
+        const uint32_t ew[4] = {ev[it].x, ev[it].y, ev[it].z, ev[it].w};
+        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
+          const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
+          acc = fma(q0, e0, acc);
+          acc = fma(q1, e1, acc);
+        }
+      }
+    }
+  } else {
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const uint4 ev = *reinterpret_cast<const uint4*>(erow + ch * 8);
+      const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
+      const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+      const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
+        const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
+        acc = fma(q0, e0, acc);
+        acc = fma(q1, e1, acc);
+      }
     }
   }
 #pragma unroll
@@ -449,7 +632,8 @@ struct SimPlan {
   int epl, cap, keep, list_max, n_res;
   size_t sel_smem;
   int tiles_m, grid;
-  size_t cand_bytes, cnt_bytes, gthr_bytes, total;
+  size_t cand_bytes, cnt_bytes, gthr_bytes, sample_bytes, total;
+  int sample_tiles;  // corpus tiles scored by the sampling pass (0 = no sampling pass)
 };
 
 constexpr size_t kSelSmemBudget = 200 * 1024;
@@ -468,34 +652,44 @@ int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
   pl->keep = k <= 100 ? 128 : 256;
   pl->epl = 16;
   pl->cap = 32 * pl->epl;
-  pl->list_max = pl->keep + 16;
   int chunk_q = nq < num_sms * kBlockM ? nq : num_sms * kBlockM;  // queries per launch
   pl->tiles_m = ceil_div(chunk_q, kBlockM);
   int n_seg = num_sms / pl->tiles_m;
-  // stage 2 keeps one query's lists in shared memory
+  // stage 2 keeps one query's lists in shared memory: full-length lists if they fit, else lists
+  // compacted to KEEP+16 at the end of stage 1, else fewer stage-1 CTAs per query block
+  // (short lists => small stage-2 footprint => several stage-2 CTAs per SM to hide the gather latency)
+  pl->list_max = pl->cap;
+  while (pl->list_max > pl->keep + 16 && sel_smem_bytes(d, n_seg, pl->list_max) > (size_t)46 << 10) pl->list_max -= 8;
   while (n_seg > 1 && sel_smem_bytes(d, n_seg, pl->list_max) > kSelSmemBudget) --n_seg;
   pl->grid = n_seg * pl->tiles_m;
   pl->sel_smem = sel_smem_bytes(d, n_seg, pl->list_max);
   pl->cand_bytes = align_up((size_t)pl->grid * kBlockM * pl->cap * sizeof(uint2), 256);
   pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);
   pl->gthr_bytes = align_up((size_t)pl->tiles_m * kBlockM * sizeof(uint32_t), 256);
-  pl->total = pl->cand_bytes + pl->cnt_bytes + pl->gthr_bytes;
+  // sampling pass: up to 32 tiles (8192 premises), score matrix capped at 64 MB
+  pl->sample_tiles = 32;
+  while (pl->sample_tiles > 4 &&
+         (size_t)pl->tiles_m * kBlockM * pl->sample_tiles * kSimBlockN * sizeof(float) > (size_t)64 << 20)
+    pl->sample_tiles /= 2;
+  pl->sample_bytes = align_up((size_t)pl->tiles_m * kBlockM * pl->sample_tiles * kSimBlockN * sizeof(float), 256);
+  pl->total = pl->cand_bytes + pl->cnt_bytes + 3 * pl->gthr_bytes + pl->sample_bytes;  // + gthr, gmin, gcnt
   return RPX_OK;
 }
 
 // Launch of stage 1 with the plan's (fixed) tiles_m / grid.  The A tensor map covers the true
 // nq rows, so query rows beyond nq are zero-filled by TMA and flagged inactive in the epilogue.
-template <int EPL, int KEEP>
-int launch_sim(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n, int d,
-               const typename EpiSimTopk<EPL, KEEP>::Params& ep, const SimPlan& pl, cudaStream_t st) {
-  using Epi = EpiSimTopk<EPL, KEEP>;
+// `tiles_n_override` / `stride`: visit only tiles 0, stride, 2*stride, ... (the sampling pass).
+template <class Epi>
+int launch_sim_epi(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n, int d,
+                   const typename Epi::Params& ep, const SimPlan& pl, cudaStream_t st, int tiles_n_override = 0,
+                   int stride = 1) {
   using Cfg = GemmCfg<kSimBlockN, kGemmStages>;
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   CUtensorMap tmA, tmB;
   RPX_TRY(make_tmap_bf16_2d(&tmA, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, kBlockM));
   RPX_TRY(make_tmap_bf16_2d(&tmB, E, (uint64_t)n, (uint64_t)d, (uint64_t)d, kSimBlockN));
-  const int tiles_n = (int)ceil_div64(n, kSimBlockN);
+  const int tiles_n = tiles_n_override > 0 ? tiles_n_override : (int)ceil_div64(n, kSimBlockN);
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   auto kern = gemm_tc_kernel<kSimBlockN, kGemmStages, Epi, true>;
   static thread_local int configured_dev = -1;
@@ -505,7 +699,8 @@ int launch_sim(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n
   }
   int64_t tiles = (int64_t)pl.tiles_m * tiles_n;
   const int grid = tiles < pl.grid ? (int)tiles : pl.grid;  // stays a multiple of tiles_m
-  kern<<<grid, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, ep);
+  kern<<<grid, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, stride,
+                                                ep);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }
@@ -544,6 +739,11 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
   uint2* cand = reinterpret_cast<uint2*>(d_workspace);
   int32_t* cnt = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes);
   uint32_t* gthr = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes + pl.cnt_bytes);
+  uint32_t* gcnt = gthr + pl.gthr_bytes / 4;
+  uint32_t* gmin = gcnt + pl.gthr_bytes / 4;
+  float* sample = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(gmin) + pl.gthr_bytes);
+  const int n_seg = pl.grid / pl.tiles_m;
+  const int rank_r = ceil_div(pl.keep, n_seg);
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(d_Q);
   const __nv_bfloat16* E = static_cast<const __nv_bfloat16*>(d_E);
   static thread_local int sel_configured = -1;
@@ -557,15 +757,26 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
     const int nq_c = nq - q0 < chunk_q ? nq - q0 : chunk_q;
     // (only the last chunk can be smaller; its tiles_m may shrink but the plan's grid stays valid
     //  because we keep tiles_m fixed and let the surplus query blocks be empty)
-    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + pl.gthr_bytes, st));  // cnt and gthr are adjacent
+    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + 2 * pl.gthr_bytes, st));  // cnt, gthr, gcnt are adjacent
+    RPX_CUDA_OK(cudaMemsetAsync(gmin, 0xFF, pl.gthr_bytes, st));
     const uint32_t* mask_c = d_access_mask ? d_access_mask + (size_t)q0 * mask_stride_words : nullptr;
+    const int64_t tiles_n_all = ceil_div64(n, kSimBlockN);
+    if (tiles_n_all >= 4 * (int64_t)pl.sample_tiles) {
+      // stage 0: starting thresholds from a strided sample of the corpus (overwrites gthr)
+      const int ld = pl.sample_tiles * kSimBlockN;
+      EpiSampleScores::Params sp{sample, ld, mask_c, mask_stride_words, nq_c, (int)n};
+      RPX_TRY((launch_sim_epi<EpiSampleScores>(Q + (size_t)q0 * d, nq_c, E, n, d, sp, pl, st, pl.sample_tiles,
+                                                (int)(tiles_n_all / pl.sample_tiles))));
+      sample_threshold_kernel<<<nq_c, 256, (size_t)ld * sizeof(uint32_t), st>>>(sample, ld, ld, pl.n_res, gthr);
+      RPX_CUDA_OK(cudaGetLastError());
+    }
     if (n > 0) {
       if (pl.keep == 128) {
-        EpiSimTopk<16, 128>::Params ep{cand, cnt, gthr, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
-        RPX_TRY((launch_sim<16, 128>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+        EpiSimTopk<16, 128>::Params ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        RPX_TRY((launch_sim_epi<EpiSimTopk<16, 128>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       } else {
-        EpiSimTopk<16, 256>::Params ep{cand, cnt, gthr, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
-        RPX_TRY((launch_sim<16, 256>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+        EpiSimTopk<16, 256>::Params ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+        RPX_TRY((launch_sim_epi<EpiSimTopk<16, 256>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       }
     }
     select_rescore_kernel<<<nq_c, kSelThreads, pl.sel_smem, st>>>(
