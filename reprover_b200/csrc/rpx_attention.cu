@@ -1,17 +1,23 @@
-// rpx_attention.cu — T5 self-attention over packed variable-length sequences.
+// rpx_attention.cu — T5 self-attention over packed variable-length sequences on tcgen05.
 //
 // Replaces HF T5Attention.forward (modeling_t5.py:253-344):
 //   scores = q k^T            (NO 1/sqrt(d) scaling in T5)
 //          + position_bias    (bucketed relative bias, shared by all layers; K5)
 //          + padding mask     (packed layout: keys simply stop at the sequence end)
 //   out    = softmax_fp32(scores) v, heads merged to [T, heads*64]
-// without ever materialising the [B, heads, L, L] score tensor: flash-style online
-// softmax, one CTA per (64-query tile, head, sequence), K/V streamed through a
-// double-buffered cp.async ring, QK^T and PV on the tensor cores.
+// without ever materialising the [B, heads, L, L] score tensor.
 //
-// Round-1 note: this kernel uses the legacy warp-level `mma.sync` path (HMMA).
-// Attention is 0.5-8 % of the encoder FLOPs; the tcgen05 version
-// is listed as follow-up work in DESIGN.md.
+// One CTA per (128-query tile, head, sequence), 192 threads, three CTAs per SM:
+//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  Per 64-key step: read the 64
+//              scores from TMEM, add the bias, online softmax in fp32 (single pass), write P as bf16
+//              into a 128B-swizzled K-major shared-memory tile, and rescale the output accumulator,
+//              which lives in TMEM, by exp(m_old - m_new) (tcgen05.ld / st) when the row max moved.
+//   warp 4     MMA issuer: S = Q K^T (tcgen05.mma M128 N64 K16 x4) and O += P V (x4; V is the
+//              MN-major B operand straight from the [keys, 64] tile TMA delivered), completion
+//              signalled with tcgen05.commit.
+//   warp 5     TMA loader: Q once, then double-buffered K / V tiles, through tensor maps over the
+//              packed qkv activation matrix (box 64 columns x 128 / 64 rows).
+// S(j+1) is issued right behind PV(j), so the next scores are ready when the softmax warps return.
 #include "rpx_common.cuh"
 #include "rpx_kernels.cuh"
 #include "rpx_ptx.cuh"
@@ -20,254 +26,332 @@ namespace rpx {
 
 namespace {
 
-constexpr int kHD = 64;      // head dim (d_kv)
-constexpr int kQT = 64;      // query rows per CTA
-constexpr int kKT = 64;      // keys per pipeline step
-constexpr int kAttnThreads = 128;
+constexpr int kHD = 64;    // head dim (d_kv)
+constexpr int kQT = 128;   // query rows per CTA (UMMA M)
+constexpr int kKT = 64;    // keys per step (UMMA N for S, K extent for PV)
+constexpr int kAttnThreads = 192;
+constexpr int kQBytes = 128 * 128;  // [128 rows][64 bf16], 128B-swizzled
+constexpr int kKVBytes = 64 * 128;  // [64 keys][64 bf16]
+constexpr int kCtasPerSm = 3;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t dst = smem_u32(smem_dst);
-  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+// smem map (bytes, 1024-aligned base): Q | K0 K1 | V0 V1 | P | bias | barriers  (~66 KB: 3 CTAs / SM)
+constexpr int kOffQ = 0;
+constexpr int kOffK = kQBytes;
+constexpr int kOffV = kQBytes + 2 * kKVBytes;
+constexpr int kOffP = kQBytes + 4 * kKVBytes;
+constexpr int kOffBias = 2 * kQBytes + 4 * kKVBytes;
+constexpr int kAttnSmemFixed = kOffBias;
+
+// MN-major (N contiguous) bf16 operand stored as rows of 128 B with the 128-byte swizzle:
+// canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements — one 64-element atom along N
+// (m = 1, LBO unused), groups of 8 K-rows 1024 B apart (SBO).  Same bit layout as the K-major
+// descriptor; the "major" lives in the instruction descriptor.
+RPX_DEVICE uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// 2^x on the SFU (one MUFU.EX2; -inf -> 0, denormal results flushed).
+RPX_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// idesc with B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t m, uint32_t n) {
+  return make_idesc_bf16(m, n) | (1u << 16);
 }
 
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
-                                               uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// A [rows][64] bf16 tile: row r = 128 B = 8 chunks of 16 B; chunk c lives at c ^ (r & 7).
-__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
-
-// Loads `rows` x 64 bf16 from global (row pitch ld elems) into a swizzled tile; rows >= n_valid are zero.
-__device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* g, int64_t ld, int n_valid,
-                                          int tid) {
-  // 64 rows * 8 chunks = 512 chunks; 128 threads -> 4 each
+// s[j] += relative-position bias of key (key0 + j) for this row; LUT index clamp(d0 + j, 0, 2R).
+// Three regimes per (row, 32-key chunk): entirely clamped (one constant), entirely inside the table
+// (no clamp), or straddling an edge (per-element clamp; at most two chunks per row).
+RPX_DEVICE void add_bias32(float (&s)[32], const float* __restrict__ sBias, int d0, int R) {
+  if (d0 >= 2 * R || d0 + 31 <= 0) {
+    const float b = sBias[d0 >= 2 * R ? 2 * R : 0];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * kAttnThreads;
-    const int r = idx >> 3, c = idx & 7;
-    const bool ok = r < n_valid;
-    const __nv_bfloat16* src = g + (int64_t)(ok ? r : 0) * ld + c * 8;
-    cp_async16(tile + tile_off(r, c), src, ok);
+    for (int j = 0; j < 32; ++j) s[j] += b;
+  } else if (d0 >= 0 && d0 + 31 <= 2 * R) {
+    const float* bp = sBias + d0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[j] += bp[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[j] += sBias[min(max(d0 + j, 0), 2 * R)];
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads)
-t5_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                    const int32_t* __restrict__ cu_seqlens, const float* __restrict__ bias_lut,
-                    int n_heads, int R, int ld_qkv, int ld_out) {
+__global__ void __launch_bounds__(kAttnThreads, kCtasPerSm)
+t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                       __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens,
+                       const float* __restrict__ bias_lut, int n_heads, int R, int ld_out) {
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;
   const int q0 = qt * kQT;
-  if (q0 >= len) return;
+  if (q0 >= len) return;  // whole CTA
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((128 - (raw & 127)) & 127);
-  uint8_t* sQ = smem;                 // 8 KB
-  uint8_t* sK = smem + 8192;          // 2 x 8 KB
-  uint8_t* sV = smem + 8192 * 3;      // 2 x 8 KB
-  float* sBias = reinterpret_cast<float*>(smem + 8192 * 5);  // 2R+1 floats
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  float* sBias = reinterpret_cast<float*>(smem + kOffBias);
+  const int lut_w = 2 * R + 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBias + ((lut_w * 4 + 15) & ~15));
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k_full = bars + 1;   // [2]
+  uint64_t* bar_k_free = bars + 3;   // [2]
+  uint64_t* bar_v_full = bars + 5;   // [2]
+  uint64_t* bar_v_free = bars + 7;   // [2]
+  uint64_t* bar_s_full = bars + 9;
+  uint64_t* bar_p_ready = bars + 10;
+  uint64_t* bar_o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = n_heads * kHD;
-
-  const __nv_bfloat16* qbase = qkv + (int64_t)t0 * ld_qkv + head * kHD;
-  const __nv_bfloat16* kbase = qbase + inner;
-  const __nv_bfloat16* vbase = qbase + 2 * inner;
-
-  for (int i = tid; i < 2 * R + 1; i += kAttnThreads) sBias[i] = bias_lut[head * (2 * R + 1) + i];
-
-  load_tile(sQ, qbase + (int64_t)q0 * ld_qkv, ld_qkv, len - q0 < kQT ? len - q0 : kQT, tid);
-  cp_async_commit();
   const int n_kt = (len + kKT - 1) / kKT;
-  {
-    const int nv = len < kKT ? len : kKT;
-    load_tile(sK, kbase, ld_qkv, nv, tid);
-    load_tile(sV, vbase, ld_qkv, nv, tid);
-    cp_async_commit();
-  }
 
-  // Q fragments for this warp's 16 rows (4 k-steps of 16 dims)
-  cp_async_wait<1>();
+  if (threadIdx.x < 128)
+    for (int i = threadIdx.x; i < lut_w; i += 128) sBias[i] = bias_lut[head * lut_w + i];
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_init(bar_q, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bar_k_full[s], 1);
+        mbar_init(&bar_k_free[s], 1);
+        mbar_init(&bar_v_full[s], 1);
+        mbar_init(&bar_v_free[s], 1);
+      }
+      mbar_init(bar_s_full, 1);
+      mbar_init(bar_p_ready, 128);
+      mbar_init(bar_o_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 128);  // S: columns [0,64), O: [64,128)
+  }
+  if (warp == 5 && elect_one()) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+  }
+  tc_fence_before();
   __syncthreads();
-  uint32_t qf[4][4];
-  {
-    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
-  }
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
-  const float kLog2e = 1.4426950408889634f;
-  float m_run[2] = {-INFINITY, -INFINITY};
-  float l_run[2] = {0.f, 0.f};
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-
-  const int row_lo = q0 + warp * 16 + g;  // sequence-relative query position of c0/c1 (c2/c3: +8)
-
-  for (int kt = 0; kt < n_kt; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < n_kt) {
-      const int kb1 = (kt + 1) * kKT;
-      const int nv = len - kb1 < kKT ? len - kb1 : kKT;
-      load_tile(sK + (buf ^ 1) * 8192, kbase + (int64_t)kb1 * ld_qkv, ld_qkv, nv, tid);
-      load_tile(sV + (buf ^ 1) * 8192, vbase + (int64_t)kb1 * ld_qkv, ld_qkv, nv, tid);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-
-    const uint32_t kT = smem_u32(sK + buf * 8192);
-    const uint32_t vT = smem_u32(sV + buf * 8192);
-    const int kb = kt * kKT;
-
-    // ---- S = Q K^T  (16 x 64 per warp)
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int nbp = 0; nbp < 4; ++nbp) {
-        uint32_t kf[4];
-        const int r = nbp * 16 + (lane & 7) + (lane >> 4) * 8;
-        ldmatrix_x4(kf, kT + tile_off(r, ks * 2 + ((lane >> 3) & 1)));
-        mma_bf16_16816(s[2 * nbp], qf[ks], kf[0], kf[1]);
-        mma_bf16_16816(s[2 * nbp + 1], qf[ks], kf[2], kf[3]);
+  if (warp == 5) {
+    // ------------------------------------------------------------------ TMA loader
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_q, kQBytes);
+      tma_load_2d(smem + kOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int b = kt & 1;
+        if (kt >= 2) mbar_wait(&bar_k_free[b], ((kt >> 1) - 1) & 1, 11);   // S(kt-2) has read K[b]
+        mbar_arrive_expect_tx(&bar_k_full[b], kKVBytes);
+        tma_load_2d(smem + kOffK + b * kKVBytes, &tm_kv, &bar_k_full[b], inner + head * kHD, t0 + kt * kKT);
+        if (kt >= 2) mbar_wait(&bar_v_free[b], ((kt >> 1) - 1) & 1, 18);   // PV(kt-2) has read V[b]
+        mbar_arrive_expect_tx(&bar_v_full[b], kKVBytes);
+        tma_load_2d(smem + kOffV + b * kKVBytes, &tm_kv, &bar_v_full[b], 2 * inner + head * kHD, t0 + kt * kKT);
       }
     }
-
-    // ---- + relative-position bias, key mask, online softmax (fp32)
-    float m_new[2] = {m_run[0], m_run[1]};
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(kQT, kKT);      // S[128 x 64]  = Q[128 x 64] K[64 x 64]^T
+      const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);  // O[128 x 64] += P[128 x 64] V[64 x 64]
+      const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffQ));
+      const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffP));
+      mbar_wait(bar_q, 0, 12);
+      mbar_wait(&bar_k_full[0], 0, 13);
+      tc_fence_after();
+      {
+        const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK));
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+        for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+      }
+      umma_commit(bar_s_full);
+      umma_commit(&bar_k_free[0]);
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int b = kt & 1;
+        // O += P(kt) V(kt): needs P(kt) written (and O rescaled) and V(kt) landed
+        mbar_wait(bar_p_ready, kt & 1, 14);
+        mbar_wait(&bar_v_full[b], (kt >> 1) & 1, 19);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(smem + kOffV + b * kKVBytes);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = kb + nb * 8 + 2 * t + (e & 1);
-        const int row = row_lo + (e >> 1) * 8;
-        int d = key - row;
-        d = d < -R ? -R : (d > R ? R : d);
-        float v = s[nb][e] + sBias[d + R];
-        v = key < len ? v : -INFINITY;
-        s[nb][e] = v;
-        m_new[e >> 1] = fmaxf(m_new[e >> 1], v);
+        for (int k = 0; k < kKT / 16; ++k) {
+          // B = V (MN-major): 16 keys = two 8-row groups = 2048 B per step; A = P: 32 B per step
+          const uint64_t v_desc = make_smem_desc_mnmajor_sw128(v_base + k * 2048);
+          umma_bf16_ss(tmem_O, p_desc + 2 * k, v_desc, idesc_o, (kt | k) != 0);
+        }
+        umma_commit(bar_o_full);
+        umma_commit(&bar_v_free[b]);
+        // S(kt+1): the softmax warps are done with S(kt) (they signalled p_ready(kt))
+        if (kt + 1 < n_kt) {
+          const int b1 = (kt + 1) & 1;
+          mbar_wait(&bar_k_full[b1], ((kt + 1) >> 1) & 1, 15);
+          tc_fence_after();
+          const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK + b1 * kKVBytes));
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_s_full);
+          umma_commit(&bar_k_free[b1]);
+        }
       }
     }
+  } else {
+    // ------------------------------------------------------------------ softmax / output warps
+    const int row = warp * 32 + lane;        // TMEM lane == query row inside the tile
+    const int qpos = q0 + row;               // position inside the sequence
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const bool warp_live = q0 + warp * 32 < len;  // warp-uniform: some row of this warp is inside the sequence
+    const float kLog2e = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + kOffP + row * 128;
+
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int kb = kt * kKT;
+      mbar_wait(bar_s_full, kt & 1, 16);
+      tc_fence_after();
+      float scale = 1.f;
+      if (warp_live) {
+        // ---- single pass over the 64 scores of this row
+        float s0[32], s1[32];
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_S + lane_addr, v);
+          tmem_ld_wait();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      m_new[h] = fmaxf(m_new[h], __shfl_xor_sync(0xffffffffu, m_new[h], 1));
-      m_new[h] = fmaxf(m_new[h], __shfl_xor_sync(0xffffffffu, m_new[h], 2));
-    }
-    float scale[2], mb[2];
+          for (int j = 0; j < 32; ++j) s0[j] = (kb + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+          add_bias32(s0, sBias, kb - qpos + R, R);
+        }
+        const bool second = kb + 32 < len;  // CTA-uniform
+        if (second) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_S + lane_addr + 32, v);
+          tmem_ld_wait();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      // every tile holds at least one valid key, so m_new is finite from the first tile on
-      scale[h] = exp2f((m_run[h] - m_new[h]) * kLog2e);
-      mb[h] = m_new[h] * kLog2e;
-      m_run[h] = m_new[h];
-      l_run[h] *= scale[h];
-    }
-    uint32_t pf[4][4];  // P as A fragments for the 4 k-steps (16 keys each) of PV
+          for (int j = 0; j < 32; ++j) s1[j] = (kb + 32 + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+          add_bias32(s1, sBias, kb + 32 - qpos + R, R);
+        } else {
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      float p0 = exp2f(s[nb][0] * kLog2e - mb[0]);
-      float p1 = exp2f(s[nb][1] * kLog2e - mb[0]);
-      float p2 = exp2f(s[nb][2] * kLog2e - mb[1]);
-      float p3 = exp2f(s[nb][3] * kLog2e - mb[1]);
-      l_run[0] += p0 + p1;
-      l_run[1] += p2 + p3;
-      const int kk = nb >> 1, hi = nb & 1;
-      pf[kk][hi * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[kk][hi * 2 + 1] = pack_bf16x2(p2, p3);
-    }
+          for (int j = 0; j < 32; ++j) s1[j] = -INFINITY;
+        }
+        float m_new = m_run;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i][0] *= scale[0];
-      o[i][1] *= scale[0];
-      o[i][2] *= scale[1];
-      o[i][3] *= scale[1];
+        for (int j = 0; j < 32; ++j) m_new = fmaxf(m_new, fmaxf(s0[j], s1[j]));
+        const float mb = m_new * kLog2e;
+        scale = fast_exp2((m_run - m_new) * kLog2e);  // 0 on the first step (m_run = -inf)
+        float l_add = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = fast_exp2(fmaf(h ? s1[j] : s0[j], kLog2e, -mb));
+            const float p1 = fast_exp2(fmaf(h ? s1[j + 1] : s0[j + 1], kLog2e, -mb));
+            l_add += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+          }
+          // keys [32h, 32h+32) = 16-byte slots 4h..4h+3 of this row's 128-byte line
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int slot = (h * 4 + s4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(prow + slot * 16) =
+                make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+          }
+        }
+        m_run = m_new;
+        l_run = l_run * scale + l_add;
+      } else {
+#pragma unroll
+        for (int s4 = 0; s4 < 8; ++s4) *reinterpret_cast<uint4*>(prow + s4 * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      // ---- O (in TMEM) *= exp(m_old - m_new) before PV(kt) accumulates onto it
+      if (kt > 0) {
+        mbar_wait(bar_o_full, (kt - 1) & 1, 17);  // PV(kt-1) has retired
+        tc_fence_after();
+        if (warp_live && !__all_sync(0xffffffffu, scale == 1.f)) {
+#pragma unroll
+          for (int c = 0; c < kHD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * scale);
+            tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
     }
 
-    // ---- O += P V
+    mbar_wait(bar_o_full, (n_kt - 1) & 1, 20);
+    tc_fence_after();
+    if (warp_live) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = out + (int64_t)(t0 + qpos) * ld_out + head * kHD;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+      for (int c = 0; c < kHD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qpos < len) {
 #pragma unroll
-      for (int dbp = 0; dbp < 4; ++dbp) {
-        uint32_t vf[4];
-        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4_trans(vf, vT + tile_off(r, dbp * 2 + (lane >> 4)));
-        mma_bf16_16816(o[2 * dbp], pf[kk], vf[0], vf[1]);
-        mma_bf16_16816(o[2 * dbp + 1], pf[kk], vf[2], vf[3]);
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(dst + c * 32)[i] = w;
+          }
+        }
       }
     }
-    __syncthreads();  // all warps done with this buffer before it is refilled
   }
 
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
-    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
-  }
-  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-  const int r0 = row_lo, r1 = row_lo + 8;
-  __nv_bfloat16* obase = out + (int64_t)t0 * ld_out + head * kHD;
-#pragma unroll
-  for (int db = 0; db < 8; ++db) {
-    const int col = db * 8 + 2 * t;
-    if (r0 < len)
-      *reinterpret_cast<uint32_t*>(obase + (int64_t)r0 * ld_out + col) = pack_bf16x2(o[db][0] * inv0, o[db][1] * inv0);
-    if (r1 < len)
-      *reinterpret_cast<uint32_t*>(obase + (int64_t)r1 * ld_out + col) = pack_bf16x2(o[db][2] * inv1, o[db][3] * inv1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
 }  // namespace
 
 int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens,
-                        const float* bias_lut, int n_seqs, int max_len, int n_heads, int d_kv,
+                        const float* bias_lut, int n_tokens, int n_seqs, int max_len, int n_heads, int d_kv,
                         int max_distance, cudaStream_t stream) {
   RPX_REQUIRE(d_kv == kHD, RPX_ERR_UNSUPPORTED, "attention: d_kv=%d (only 64 is implemented)", d_kv);
-  RPX_REQUIRE(n_seqs > 0 && max_len > 0, RPX_ERR_INVALID, "attention: empty batch");
+  RPX_REQUIRE(n_seqs > 0 && max_len > 0 && n_tokens > 0, RPX_ERR_INVALID, "attention: empty batch");
   RPX_REQUIRE(n_seqs <= 65535 && n_heads <= 65535, RPX_ERR_UNSUPPORTED, "attention: grid limits exceeded");
   const int inner = n_heads * d_kv;
-  const size_t smem = 8192 * 5 + (size_t)(2 * max_distance + 1) * sizeof(float) + 128;
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  CUtensorMap tm_q, tm_kv;
+  RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kQT));
+  RPX_TRY(make_tmap_bf16_2d(&tm_kv, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kKT));
+  const size_t smem = 1024 + kAttnSmemFixed + (((size_t)(2 * max_distance + 1) * 4 + 15) & ~(size_t)15) + 128;
+  RPX_REQUIRE(smem <= 100 * 1024, RPX_ERR_UNSUPPORTED, "attention: bias table too large (%zu B of shared memory)", smem);
   static thread_local int configured = -1;
-  int dev = 0;
-  RPX_CUDA_OK(cudaGetDevice(&dev));
-  if (configured != dev) {
-    RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = dev;
+  if (configured != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = dev.device;
   }
-  RPX_REQUIRE(smem <= 64 * 1024, RPX_ERR_UNSUPPORTED, "attention: bias table too large");
   dim3 grid((max_len + kQT - 1) / kQT, n_heads, n_seqs);
-  t5_attention_kernel<<<grid, kAttnThreads, smem, stream>>>(qkv, out, cu_seqlens, bias_lut, n_heads,
-                                                            max_distance, 3 * inner, inner);
+  t5_attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tm_q, tm_kv, out, cu_seqlens, bias_lut, n_heads,
+                                                               max_distance, inner);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }

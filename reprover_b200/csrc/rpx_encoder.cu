@@ -232,7 +232,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     }
     {
       Prof p(e, st, 2);
-      RPX_TRY(launch_t5_attention(ws.qkv, ws.attn, ws.cu_tokens, e->bias_lut, S, max_len, c.num_heads, c.d_kv,
+      RPX_TRY(launch_t5_attention(ws.qkv, ws.attn, ws.cu_tokens, e->bias_lut, T, S, max_len, c.num_heads, c.d_kv,
                                   c.rel_max_distance, st));
     }
     {

@@ -11,7 +11,7 @@ namespace rpx {
 // qkv [T, 3*heads*d_kv] bf16 packed tokens; out [T, heads*d_kv] bf16;
 // bias_lut [heads][2*max_distance+1] fp32, entry (delta + max_distance), delta = key - query clamped.
 int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens,
-                        const float* bias_lut, int n_seqs, int max_len, int n_heads, int d_kv,
+                        const float* bias_lut, int n_tokens, int n_seqs, int max_len, int n_heads, int d_kv,
                         int max_distance, cudaStream_t stream);
 
 // ---- rpx_elementwise.cu
