@@ -183,6 +183,9 @@ int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_par
  * C[M, N] (fp32, ldc = N) = A[M, K] * B[N, K]^T, bf16 inputs; K % 64 == 0, N % 32 == 0. */
 int rpx_gemm_bf16_f32(const void* d_A, const void* d_B, float* d_C, int32_t M, int32_t N,
                       int32_t K, void* stream);
+/* Same contract through the 2-CTA (cta_group::2, 256 x 256 tile) form of the core. */
+int rpx_gemm2_bf16_f32(const void* d_A, const void* d_B, float* d_C, int32_t M, int32_t N,
+                       int32_t K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,20 @@ namespace {
 
 constexpr int kBlockN = 256;
 
+#ifndef RPX_GEMM_2CTA
+#define RPX_GEMM_2CTA 1
+#endif
+// The encoder's GEMMs: 2-CTA (cta_group::2) tiles by default, the 1-CTA kernel with -DRPX_GEMM_2CTA=0.
+template <class Epi>
+int encoder_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                 const typename Epi::Params& ep, cudaStream_t st) {
+#if RPX_GEMM_2CTA
+  return launch_gemm2<Epi>(A, lda, B, ldb, M, N, K, ep, st);
+#else
+  return launch_gemm<kBlockN, Epi>(A, lda, B, ldb, M, N, K, ep, st);
+#endif
+}
+
 struct LayerW {
   const __nv_bfloat16* qkv;  // [3*inner, D]   (ln0 folded)
   const __nv_bfloat16* o;    // [D, inner]
@@ -228,7 +242,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     {
       Prof p(e, st, 1);
       EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
-      RPX_TRY((launch_gemm<kBlockN, EpiStoreBF16>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st)));
+      RPX_TRY((encoder_gemm<EpiStoreBF16>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st)));
     }
     {
       Prof p(e, st, 2);
@@ -238,17 +252,17 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     {
       Prof p(e, st, 3);
       EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
-      RPX_TRY((launch_gemm<kBlockN, EpiResidual>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+      RPX_TRY((encoder_gemm<EpiResidual>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
     }
     {
       Prof p(e, st, 4);
       EpiGeGLU::Params ep{ws.ffn, F, RowScale{ws.ssB, P, T, inv_d, c.ln_eps}};
-      RPX_TRY((launch_gemm<kBlockN, EpiGeGLU>(ws.h16, D, w.wi, D, T, 2 * F, D, ep, st)));
+      RPX_TRY((encoder_gemm<EpiGeGLU>(ws.h16, D, w.wi, D, T, 2 * F, D, ep, st)));
     }
     {
       Prof p(e, st, 5);
       EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
-      RPX_TRY((launch_gemm<kBlockN, EpiResidual>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+      RPX_TRY((encoder_gemm<EpiResidual>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
     }
     RPX_TRY(dump(l + 1));
   }

@@ -2,6 +2,7 @@
 #pragma once
 #include "rpx_common.cuh"
 #include "rpx_gemm.cuh"
+#include "rpx_gemm2.cuh"
 
 namespace rpx {
 
@@ -38,6 +39,40 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
   int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
   if (grid > cap) grid = cap;
   kern<<<grid, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, 1, ep);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+
+constexpr int kGemm2Stages = 6;
+
+// 2-CTA (cta_group::2) launcher: 256 x 256 tiles, one CTA pair per tile, persistent over num_sms/2 pairs.
+template <class Epi>
+int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                 const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<kGemm2Stages>;
+  RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
+  RPX_REQUIRE(N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  CUtensorMap tmA, tmB;
+  RPX_TRY(make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockM));
+  RPX_TRY(make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, Cfg::kBlockN / 2));
+  const int tiles_m = ceil_div(M, kPairM);
+  const int tiles_n = ceil_div(N, Cfg::kBlockN);
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "gemm2: needs %zu B smem, device allows %zu", smem,
+              dev.smem_optin);
+  auto kern = gemm_tc2_kernel<kGemm2Stages, Epi>;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev.device;
+  }
+  int pairs = tiles_m * tiles_n;
+  if (pairs > dev.num_sms / 2) pairs = dev.num_sms / 2;
+  kern<<<2 * pairs, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, ep);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }

@@ -10,12 +10,23 @@ from reprover_b200 import _native
 pytestmark = pytest.mark.gpu
 
 
+ENTRY = "rpx_gemm_bf16_f32"
+
+
+@pytest.fixture(params=["rpx_gemm_bf16_f32", "rpx_gemm2_bf16_f32"], autouse=True)
+def _entry(request):
+    """Every test runs through both the 1-CTA and the 2-CTA (cta_group::2) form of the core."""
+    global ENTRY
+    ENTRY = request.param
+    yield
+
+
 def _run_gemm(lib, A, B):
     M, K = A.shape
     N = B.shape[0]
     Cout = torch.full((M, N), float("nan"), device=A.device, dtype=torch.float32)
     st = torch.cuda.current_stream().cuda_stream
-    _native.check(lib.rpx_gemm_bf16_f32(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), M, N, K, st))
+    _native.check(getattr(lib, ENTRY)(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), M, N, K, st))
     torch.cuda.synchronize()
     return Cout
 
@@ -85,6 +96,6 @@ def test_gemm_rejects_bad_shapes(rpx_lib, cuda_device):
     B = torch.zeros(256, 100, dtype=torch.bfloat16, device=cuda_device)
     C = torch.zeros(128, 256, device=cuda_device)
     st = torch.cuda.current_stream().cuda_stream
-    rc = rpx_lib.rpx_gemm_bf16_f32(A.data_ptr(), B.data_ptr(), C.data_ptr(), 128, 256, 100, st)
+    rc = getattr(rpx_lib, ENTRY)(A.data_ptr(), B.data_ptr(), C.data_ptr(), 128, 256, 100, st)
     assert rc == _native.RPX_ERR_UNSUPPORTED
     assert "multiple of 64" in _native.last_error()
