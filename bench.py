@@ -307,7 +307,7 @@ def run_engine(args) -> dict:
                    "parallelism": f"row-sharded corpus x{world}, no data-path collective in reindex",
                    "l2": "inputs larger than L2 (fresh premises every step; ~19 KB activations/token)",
                    "max_tokens_per_call": args.max_tokens_per_call},
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4,EpiGeGLU> (FFN up-projection, 58% of FLOPs)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<6,EpiGeGLU> (FFN up-projection, 2-CTA tcgen05, 58% of FLOPs)",
                      "achieved": ffn_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": ffn_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
                      "traffic": traffic, "launches": ffn["launches"], "avg_launch_ms": ffn["ms"] / max(ffn["launches"], 1)},

@@ -40,6 +40,9 @@ constexpr int kUmmaK = 16;
 #ifndef RPX_TMA_HINTS
 #define RPX_TMA_HINTS 0
 #endif
+#ifndef RPX_EPI_HINTS
+#define RPX_EPI_HINTS 0
+#endif
 #ifndef RPX_EPI_WARPS
 #define RPX_EPI_WARPS 4
 #endif
@@ -386,7 +389,9 @@ struct EpiResidual {
   Params p;
   float4* stg;  // this warp's staging tile: row r = 8 float4, stored at slot (j ^ (r & 7))
   int lane, grp;
+  uint64_t pol;
   __device__ EpiResidual(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
+    pol = l2_policy_evict_first();
     lane = row & 31;
     grp = row >> 5;
     stg = reinterpret_cast<float4*>(smem_extra) + (part * 4 + grp) * 32 * 8;
@@ -410,7 +415,11 @@ struct EpiResidual {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = row_base + sub + 4 * i;
+#if RPX_EPI_HINTS
+      if (m < t.M) h[i] = ld_f4_hint(p.h32 + (size_t)m * p.ld + col, pol);
+#else
       if (m < t.M) h[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
+#endif
       else h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -450,7 +459,11 @@ struct EpiResidual {
         h[i].w += a.w;
         ss[i] += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
         if (m < t.M) {
+#if RPX_EPI_HINTS
+          st_f4_hint(p.h32 + (size_t)m * p.ld + col, h[i], pol);
+#else
           *reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + col) = h[i];
+#endif
           *reinterpret_cast<uint2*>(p.h16 + (size_t)m * p.ld + col) =
               make_uint2(pack_bf16x2(h[i].x, h[i].y), pack_bf16x2(h[i].z, h[i].w));
         }
