@@ -366,14 +366,24 @@ sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_r
     if (tid == 0) gthr[q] = 0u;
     return;
   }
-  // largest T with count(key >= T) >= n_res
-  uint64_t lo = (uint64_t)kNegInf + 1, hi = (uint64_t)kmax + 1;  // count(>= lo) = valid >= n_res; count(>= hi) = 0
-  while (hi - lo > 1) {
+  // a T with n_res <= count(key >= T) <= n_res + 16 (any T with count >= n_res is a valid bound;
+  // the slack saves most of the bisection steps).  Start from the smallest valid key.
+  uint32_t kmin = 0xFFFFFFFFu;
+  for (int i = tid; i < n_cols; i += 256) kmin = (keys[i] > kNegInf && keys[i] < kmin) ? keys[i] : kmin;
+  kmin = block_reduce<uint32_t>(kmin, redu, [](uint32_t a, uint32_t b) { return a < b ? a : b; }, 0xFFFFFFFFu);
+  uint64_t lo = kmin, hi = (uint64_t)kmax + 1;  // count(>= lo) = valid >= n_res; count(>= hi) = 0
+  int count_lo = valid;
+  while (count_lo > n_res + 16 && hi - lo > 1) {
     const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
     int m = 0;
     for (int i = tid; i < n_cols; i += 256) m += keys[i] >= mid ? 1 : 0;
     m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
-    if (m >= n_res) lo = mid; else hi = mid;
+    if (m >= n_res) {
+      lo = mid;
+      count_lo = m;
+    } else {
+      hi = mid;
+    }
   }
   if (tid == 0) gthr[q] = (uint32_t)lo - 1u;
 }
@@ -435,7 +445,7 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
   return acc;
 }
 
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 512;
 constexpr int kSelMax = 288;  // >= largest re-score set (k + margin + selection slack)
 
 __device__ __forceinline__ uint64_t ckey(uint2 e) {
