@@ -150,10 +150,10 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       tma_load_2d(smem + kOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
       for (int kt = 0; kt < n_kt; ++kt) {
         const int b = kt & 1;
-        if (kt >= 2) mbar_wait(&bar_k_free[b], ((kt >> 1) - 1) & 1, 11);   // S(kt-2) has read K[b]
+        if (kt >= 2) mbar_wait<0>(&bar_k_free[b], ((kt >> 1) - 1) & 1, 11);   // S(kt-2) has read K[b]
         mbar_arrive_expect_tx(&bar_k_full[b], kKVBytes);
         tma_load_2d(smem + kOffK + b * kKVBytes, &tm_kv, &bar_k_full[b], inner + head * kHD, t0 + kt * kKT);
-        if (kt >= 2) mbar_wait(&bar_v_free[b], ((kt >> 1) - 1) & 1, 18);   // PV(kt-2) has read V[b]
+        if (kt >= 2) mbar_wait<0>(&bar_v_free[b], ((kt >> 1) - 1) & 1, 18);   // PV(kt-2) has read V[b]
         mbar_arrive_expect_tx(&bar_v_full[b], kKVBytes);
         tma_load_2d(smem + kOffV + b * kKVBytes, &tm_kv, &bar_v_full[b], 2 * inner + head * kHD, t0 + kt * kKT);
       }
@@ -165,8 +165,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);  // O[128 x 64] += P[128 x 64] V[64 x 64]
       const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffQ));
       const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffP));
-      mbar_wait(bar_q, 0, 12);
-      mbar_wait(&bar_k_full[0], 0, 13);
+      mbar_wait<0>(bar_q, 0, 12);
+      mbar_wait<0>(&bar_k_full[0], 0, 13);
       tc_fence_after();
       {
         const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK));
@@ -178,8 +178,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       for (int kt = 0; kt < n_kt; ++kt) {
         const int b = kt & 1;
         // O += P(kt) V(kt): needs P(kt) written (and O rescaled) and V(kt) landed
-        mbar_wait(bar_p_ready, kt & 1, 14);
-        mbar_wait(&bar_v_full[b], (kt >> 1) & 1, 19);
+        mbar_wait<0>(bar_p_ready, kt & 1, 14);
+        mbar_wait<0>(&bar_v_full[b], (kt >> 1) & 1, 19);
         tc_fence_after();
         const uint32_t v_base = smem_u32(smem + kOffV + b * kKVBytes);
 #pragma unroll
@@ -193,7 +193,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         // S(kt+1): the softmax warps are done with S(kt) (they signalled p_ready(kt))
         if (kt + 1 < n_kt) {
           const int b1 = (kt + 1) & 1;
-          mbar_wait(&bar_k_full[b1], ((kt + 1) >> 1) & 1, 15);
+          mbar_wait<0>(&bar_k_full[b1], ((kt + 1) >> 1) & 1, 15);
           tc_fence_after();
           const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK + b1 * kKVBytes));
 #pragma unroll
@@ -215,7 +215,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
     for (int kt = 0; kt < n_kt; ++kt) {
       const int kb = kt * kKT;
-      mbar_wait(bar_s_full, kt & 1, 16);
+      mbar_wait<0>(bar_s_full, kt & 1, 16);
       tc_fence_after();
       float scale = 1.f;
       if (warp_live) {
@@ -273,7 +273,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
       // ---- O (in TMEM) *= exp(m_old - m_new) before PV(kt) accumulates onto it
       if (kt > 0) {
-        mbar_wait(bar_o_full, (kt - 1) & 1, 17);  // PV(kt-1) has retired
+        mbar_wait<0>(bar_o_full, (kt - 1) & 1, 17);  // PV(kt-1) has retired
         tc_fence_after();
         if (warp_live && !__all_sync(0xffffffffu, scale == 1.f)) {
 #pragma unroll
@@ -294,7 +294,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       mbar_arrive(bar_p_ready);
     }
 
-    mbar_wait(bar_o_full, (n_kt - 1) & 1, 20);
+    mbar_wait<0>(bar_o_full, (n_kt - 1) & 1, 20);
     tc_fence_after();
     if (warp_live) {
       const float inv = 1.f / l_run;

@@ -54,40 +54,44 @@ RPX_DEVICE void mbar_arrive(uint64_t* bar) {
 #ifndef RPX_WAIT_HINT_NS
 #define RPX_WAIT_HINT_NS 2000
 #endif
-RPX_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// One mbarrier.try_wait probe.  HINT_NS > 0 adds a suspend-time hint: a failed probe may park the
+// thread for up to that long (ptxas emits NANOSLEEP.SYNCS), which frees issue slots for the other
+// warps of the sub-partition — good for the long waits of the GEMM pipelines (sim kernel: -19 %),
+// bad for short latency-critical handshakes (attention), which use HINT_NS = 0.
+template <uint32_t HINT_NS>
+RPX_DEVICE uint32_t mbar_try_wait_t(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-#if RPX_WAIT_HINT_NS > 0
-  // suspend-time hint: the thread may sleep in hardware up to this long before re-polling
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)RPX_WAIT_HINT_NS)
-      : "memory");
-#else
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-#endif
+  if constexpr (HINT_NS > 0) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(HINT_NS)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok;
 }
-// Bounded wait.  `tag` identifies the call site in the trap message.  try_wait suspends the
-// thread in hardware for a bounded time, so the loop body is kept to the bare minimum: these
-// single-thread spin loops share their SM sub-partition's issue slots with an epilogue warp.
+// Bounded wait.  `tag` identifies the call site in the trap message.  The loop body is kept to
+// the bare minimum: these spin loops share their SM sub-partition's issue slots with other warps.
+template <uint32_t HINT_NS = RPX_WAIT_HINT_NS>
 RPX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait_t<HINT_NS>(bar, parity)) return;
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_t<HINT_NS>(bar, parity)) {
     if ((++spins & 0x3FFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;

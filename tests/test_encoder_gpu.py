@@ -124,3 +124,33 @@ def test_byt5_small_cfg1(rpx_lib, cuda_device, out_dir):
     sims_got = (got[8:] @ got[:8].t()).cpu()
     sims_want = want[8:] @ want[:8].t()
     assert torch.allclose(sims_got, sims_want, atol=4e-3)
+
+
+def test_long_sequences_and_max_len_2048(rpx_lib, cuda_device, tiny):
+    """The reference indexes with max_seq_len = 2048 (retrieval/index.py:33): sequences longer than the
+    relative-bias range (|delta| >= 128 saturates), multi-tile attention, truncation at 2048 incl. EOS."""
+    cfg, sd = tiny
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    lens = [2047, 2500, 1025, 700, 129]
+    rng = np.random.default_rng(8)
+    strs = [bytes(rng.choice(synth._ALPHABET, size=n).tolist()) for n in lens]
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in strs])]).astype(np.int64)
+    data = np.frombuffer(b"".join(strs), dtype=np.uint8)
+    got = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)
+    want = oracle_embeddings(cfg, sd, data, offsets, 2048, batch_size=2)
+    max_abs, min_cos = compare_embeddings(got, want)
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
+
+
+def test_many_short_sequences_and_chunking(rpx_lib, cuda_device, tiny):
+    """Hundreds of sequences split over several engine calls (token-budget chunking) == one call."""
+    cfg, sd = tiny
+    data, offsets = synth.synth_premises(700, seed=12, min_len=1, max_len=40)
+    big = T5EncoderEngine(cfg, sd, cuda_device)
+    small = T5EncoderEngine(cfg, sd, cuda_device, max_tokens_per_call=1000)
+    a = big.encode_bytes(data, offsets, 64, out_dtype=torch.float32)
+    b = small.encode_bytes(data, offsets, 64, out_dtype=torch.float32)
+    assert torch.equal(a, b)
+    want = oracle_embeddings(cfg, sd, data[: offsets[40]], offsets[:41], 64, batch_size=40)
+    max_abs, min_cos = compare_embeddings(a[:40], want)
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
