@@ -172,8 +172,9 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
                  int64_t idx_offset, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* k-way merge of per-shard results after the all-gather:
- * inputs [n_parts, nq, k] (fp64 scores, int64 global indices, idx < 0 = empty),
- * outputs the global top-k per query under the same ordering contract. */
+ * inputs [n_parts, nq, k] (fp64 scores, int64 global indices; each [part, query] row sorted under
+ * the ordering contract with its empty slots, idx < 0, at the end — exactly what rpx_sim_topk
+ * emits), outputs the global top-k per query under the same ordering contract. */
 int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_parts, int32_t nq,
                    int32_t k, float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx,
                    int32_t* d_out_count, void* stream);

@@ -612,14 +612,27 @@ topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__
   }
   atomicAdd(&n_valid, local_valid);
   __syncthreads();
+  // Every part is already sorted under the contract (valid entries first), so the global rank of
+  // an entry is its position in its own part plus, for every other part, the number of entries that
+  // beat it — found by binary search (R * log2 k steps instead of R * k).
   for (int c = tid; c < n; c += blockDim.x) {
     const int64_t ic = ix[c];
     if (ic < 0) continue;
     const double sc = s[c];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const int64_t ij = ix[j];
-      rank += (ij >= 0 && (s[j] > sc || (s[j] == sc && ij < ic))) ? 1 : 0;
+    const int own = c / k;
+    int rank = c - own * k;
+    for (int p2 = 0; p2 < n_parts; ++p2) {
+      if (p2 == own) continue;
+      const double* ps = s + p2 * k;
+      const int64_t* pi = ix + p2 * k;
+      int lo = 0, hi = k;  // first position whose entry does NOT beat (sc, ic)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int64_t im = pi[mid];
+        const bool beats = im >= 0 && (ps[mid] > sc || (ps[mid] == sc && im < ic));
+        if (beats) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
     }
     if (rank < k) {
       const size_t o = (size_t)q * k + rank;
