@@ -7,16 +7,15 @@
 //   out    = softmax_fp32(scores) v, heads merged to [T, heads*64]
 // without ever materialising the [B, heads, L, L] score tensor.
 //
-// One CTA per (128-query tile, head, sequence), 192 threads, three CTAs per SM:
+// One CTA per (128-query tile, head, sequence), 160 threads, four CTAs per SM:
 //   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  Per 64-key step: read the 64
 //              scores from TMEM, add the bias, online softmax in fp32 (single pass), write P as bf16
 //              into a 128B-swizzled K-major shared-memory tile, and rescale the output accumulator,
 //              which lives in TMEM, by exp(m_old - m_new) (tcgen05.ld / st) when the row max moved.
-//   warp 4     MMA issuer: S = Q K^T (tcgen05.mma M128 N64 K16 x4) and O += P V (x4; V is the
-//              MN-major B operand straight from the [keys, 64] tile TMA delivered), completion
-//              signalled with tcgen05.commit.
-//   warp 5     TMA loader: Q once, then double-buffered K / V tiles, through tensor maps over the
-//              packed qkv activation matrix (box 64 columns x 128 / 64 rows).
+//   warp 4     one elected thread drives both TMA and MMA: loads Q once and K / V tile by tile
+//              (tensor maps over the packed qkv activation matrix, box 64 columns x 128 / 64 rows),
+//              issues S = Q K^T (tcgen05.mma M128 N64 K16 x4) and O += P V (x4; V is the MN-major
+//              B operand straight from the [keys, 64] tile TMA delivered), tcgen05.commit signals.
 // S(j+1) is issued right behind PV(j), so the next scores are ready when the softmax warps return.
 #include "rpx_common.cuh"
 #include "rpx_kernels.cuh"
@@ -29,17 +28,19 @@ namespace {
 constexpr int kHD = 64;    // head dim (d_kv)
 constexpr int kQT = 128;   // query rows per CTA (UMMA M)
 constexpr int kKT = 64;    // keys per step (UMMA N for S, K extent for PV)
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 160;  // 4 softmax warps + 1 warp whose elected thread drives TMA and MMA
 constexpr int kQBytes = 128 * 128;  // [128 rows][64 bf16], 128B-swizzled
 constexpr int kKVBytes = 64 * 128;  // [64 keys][64 bf16]
-constexpr int kCtasPerSm = 3;
+constexpr int kCtasPerSm = 4;
 
-// smem map (bytes, 1024-aligned base): Q | K0 K1 | V0 V1 | P | bias | barriers  (~66 KB: 3 CTAs / SM)
+// smem map (bytes, 1024-aligned base): Q | K | V | P | bias | barriers  (~50 KB: 4 CTAs / SM).
+// K and V are single-buffered: K(j+1) is fetched as soon as S(j) has retired, V(j+1) as soon as PV(j)
+// has, both well before they are needed; the other three CTAs of the SM cover what latency remains.
 constexpr int kOffQ = 0;
 constexpr int kOffK = kQBytes;
-constexpr int kOffV = kQBytes + 2 * kKVBytes;
-constexpr int kOffP = kQBytes + 4 * kKVBytes;
-constexpr int kOffBias = 2 * kQBytes + 4 * kKVBytes;
+constexpr int kOffV = kQBytes + kKVBytes;
+constexpr int kOffP = kQBytes + 2 * kKVBytes;
+constexpr int kOffBias = 2 * kQBytes + 2 * kKVBytes;
 constexpr int kAttnSmemFixed = kOffBias;
 
 // MN-major (N contiguous) bf16 operand stored as rows of 128 B with the 128-byte swizzle:
@@ -101,14 +102,14 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int lut_w = 2 * R + 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBias + ((lut_w * 4 + 15) & ~15));
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k_full = bars + 1;   // [2]
-  uint64_t* bar_k_free = bars + 3;   // [2]
-  uint64_t* bar_v_full = bars + 5;   // [2]
-  uint64_t* bar_v_free = bars + 7;   // [2]
-  uint64_t* bar_s_full = bars + 9;
-  uint64_t* bar_p_ready = bars + 10;
-  uint64_t* bar_o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_k_full = bars + 1;
+  uint64_t* bar_k_free = bars + 2;
+  uint64_t* bar_v_full = bars + 3;
+  uint64_t* bar_v_free = bars + 4;
+  uint64_t* bar_s_full = bars + 5;
+  uint64_t* bar_p_ready = bars + 6;
+  uint64_t* bar_o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = n_heads * kHD;
@@ -119,12 +120,10 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 4) {
     if (elect_one()) {
       mbar_init(bar_q, 1);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&bar_k_full[s], 1);
-        mbar_init(&bar_k_free[s], 1);
-        mbar_init(&bar_v_full[s], 1);
-        mbar_init(&bar_v_free[s], 1);
-      }
+      mbar_init(bar_k_full, 1);
+      mbar_init(bar_k_free, 1);
+      mbar_init(bar_v_full, 1);
+      mbar_init(bar_v_free, 1);
       mbar_init(bar_s_full, 1);
       mbar_init(bar_p_ready, 128);
       mbar_init(bar_o_full, 1);
@@ -133,55 +132,47 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     __syncwarp();
     tmem_alloc(tmem_slot, 128);  // S: columns [0,64), O: [64,128)
   }
-  if (warp == 5 && elect_one()) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_kv);
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
-  if (warp == 5) {
-    // ------------------------------------------------------------------ TMA loader
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA + MMA driver (one thread)
     if (elect_one()) {
+      const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
       mbar_arrive_expect_tx(bar_q, kQBytes);
       tma_load_2d(smem + kOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
-      for (int kt = 0; kt < n_kt; ++kt) {
-        const int b = kt & 1;
-        if (kt >= 2) mbar_wait<0>(&bar_k_free[b], ((kt >> 1) - 1) & 1, 11);   // S(kt-2) has read K[b]
-        mbar_arrive_expect_tx(&bar_k_full[b], kKVBytes);
-        tma_load_2d(smem + kOffK + b * kKVBytes, &tm_kv, &bar_k_full[b], inner + head * kHD, t0 + kt * kKT);
-        if (kt >= 2) mbar_wait<0>(&bar_v_free[b], ((kt >> 1) - 1) & 1, 18);   // PV(kt-2) has read V[b]
-        mbar_arrive_expect_tx(&bar_v_full[b], kKVBytes);
-        tma_load_2d(smem + kOffV + b * kKVBytes, &tm_kv, &bar_v_full[b], 2 * inner + head * kHD, t0 + kt * kKT);
-      }
-    }
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_k_full, kKVBytes);
+      tma_load_2d(smem + kOffK, &tm_kv, bar_k_full, kcol, t0);
+      mbar_arrive_expect_tx(bar_v_full, kKVBytes);
+      tma_load_2d(smem + kOffV, &tm_kv, bar_v_full, vcol, t0);
+
       const uint32_t idesc_s = make_idesc_bf16(kQT, kKT);      // S[128 x 64]  = Q[128 x 64] K[64 x 64]^T
       const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);  // O[128 x 64] += P[128 x 64] V[64 x 64]
       const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffQ));
+      const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK));
       const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffP));
+      const uint32_t v_base = smem_u32(smem + kOffV);
       mbar_wait<0>(bar_q, 0, 12);
-      mbar_wait<0>(&bar_k_full[0], 0, 13);
+      mbar_wait<0>(bar_k_full, 0, 13);
       tc_fence_after();
-      {
-        const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK));
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-      }
+      for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
       umma_commit(bar_s_full);
-      umma_commit(&bar_k_free[0]);
+      umma_commit(bar_k_free);
       for (int kt = 0; kt < n_kt; ++kt) {
-        const int b = kt & 1;
+        const bool more = kt + 1 < n_kt;
+        if (more) {  // K(kt+1) as soon as S(kt) has read K(kt)
+          mbar_wait<0>(bar_k_free, kt & 1, 11);
+          mbar_arrive_expect_tx(bar_k_full, kKVBytes);
+          tma_load_2d(smem + kOffK, &tm_kv, bar_k_full, kcol, t0 + (kt + 1) * kKT);
+        }
         // O += P(kt) V(kt): needs P(kt) written (and O rescaled) and V(kt) landed
         mbar_wait<0>(bar_p_ready, kt & 1, 14);
-        mbar_wait<0>(&bar_v_full[b], (kt >> 1) & 1, 19);
+        mbar_wait<0>(bar_v_full, kt & 1, 19);
         tc_fence_after();
-        const uint32_t v_base = smem_u32(smem + kOffV + b * kKVBytes);
 #pragma unroll
         for (int k = 0; k < kKT / 16; ++k) {
           // B = V (MN-major): 16 keys = two 8-row groups = 2048 B per step; A = P: 32 B per step
@@ -189,17 +180,19 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           umma_bf16_ss(tmem_O, p_desc + 2 * k, v_desc, idesc_o, (kt | k) != 0);
         }
         umma_commit(bar_o_full);
-        umma_commit(&bar_v_free[b]);
-        // S(kt+1): the softmax warps are done with S(kt) (they signalled p_ready(kt))
-        if (kt + 1 < n_kt) {
-          const int b1 = (kt + 1) & 1;
-          mbar_wait<0>(&bar_k_full[b1], ((kt + 1) >> 1) & 1, 15);
+        umma_commit(bar_v_free);
+        if (more) {
+          // S(kt+1): the softmax warps are done with S(kt) (they signalled p_ready(kt))
+          mbar_wait<0>(bar_k_full, (kt + 1) & 1, 15);
           tc_fence_after();
-          const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK + b1 * kKVBytes));
 #pragma unroll
           for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
           umma_commit(bar_s_full);
-          umma_commit(&bar_k_free[b1]);
+          umma_commit(bar_k_free);
+          // V(kt+1) once PV(kt) has read V(kt)
+          mbar_wait<0>(bar_v_free, kt & 1, 18);
+          mbar_arrive_expect_tx(bar_v_full, kKVBytes);
+          tma_load_2d(smem + kOffV, &tm_kv, bar_v_full, vcol, t0 + (kt + 1) * kKT);
         }
       }
     }

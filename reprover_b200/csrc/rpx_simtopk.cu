@@ -342,6 +342,19 @@ struct EpiSampleScores {
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity);
 
+// Block-wide sum of per-thread counts with ONE barrier per call: warp REDUX, one shared-memory
+// atomic per warp, three rotating counters (slot i % 3 is used by call i and cleared during call
+// i + 1, well before call i + 3 adds to it again).  `slots` must be zero on the first call.
+__device__ __forceinline__ int block_count(int m, int* slots, int iter) {
+  m = __reduce_add_sync(kFull, m);
+  int* cur = slots + iter % 3;
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicAdd(cur, m);
+  __syncthreads();
+  const int total = *cur;
+  if (threadIdx.x == 0) slots[(iter + 2) % 3] = 0;
+  return total;
+}
+
 // One CTA per query: gthr[q] = (n_res-th largest sample key) - 1, or 0 when fewer than n_res
 // sampled premises are admissible.
 __global__ void __launch_bounds__(256)
@@ -373,11 +386,14 @@ sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_r
   kmin = block_reduce<uint32_t>(kmin, redu, [](uint32_t a, uint32_t b) { return a < b ? a : b; }, 0xFFFFFFFFu);
   uint64_t lo = kmin, hi = (uint64_t)kmax + 1;  // count(>= lo) = valid >= n_res; count(>= hi) = 0
   int count_lo = valid;
-  while (count_lo > n_res + 16 && hi - lo > 1) {
+  __shared__ int cslots[3];
+  if (tid < 3) cslots[tid] = 0;
+  __syncthreads();
+  for (int iter = 0; count_lo > n_res + 16 && hi - lo > 1; ++iter) {
     const uint32_t mid = (uint32_t)(lo + (hi - lo) / 2);
     int m = 0;
     for (int i = tid; i < n_cols; i += 256) m += keys[i] >= mid ? 1 : 0;
-    m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
+    m = block_count(m, cslots, iter);
     if (m >= n_res) {
       lo = mid;
       count_lo = m;
@@ -488,7 +504,7 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
   uint64_t* keys = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(seg_off + n_seg + 1) + 15) & ~(uintptr_t)15);                   // [n_seg * list_max]
   __shared__ uint64_t red64[32];
-  __shared__ int redi[32];
+  __shared__ int cslots[3];
   __shared__ int n_sel;
 
   const int q = blockIdx.x;
@@ -497,6 +513,7 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
 
   for (int i = tid; i < d / 8; i += kSelThreads)
     reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(Q + (size_t)q * d)[i];
+  if (tid < 3) cslots[tid] = 0;
   if (tid == 0) {
     n_sel = 0;
     int acc = 0;
@@ -532,11 +549,11 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
     uint64_t hi = kmax;  // count(>= kmax) = 1 < n_res
     int count_lo = total;
     // invariant: count(>= lo) = count_lo >= n_res, count(>= hi) < n_res
-    while (count_lo > n_res + 16 && hi - lo > 1) {
+    for (int iter = 0; count_lo > n_res + 16 && hi - lo > 1; ++iter) {
       const uint64_t mid = lo + (hi - lo) / 2;
       int m = 0;
       for (int i = tid; i < total; i += kSelThreads) m += keys[i] >= mid ? 1 : 0;
-      m = block_reduce<int>(m, redi, [](int a, int b) { return a + b; }, 0);
+      m = block_count(m, cslots, iter);
       if (m >= n_res) {
         lo = mid;
         count_lo = m;
