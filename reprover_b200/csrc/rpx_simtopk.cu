@@ -408,7 +408,7 @@ sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_r
 
 // Canonical fp64 dot product (identical in oracle/rpx_oracle.c::rpx_oracle_dot64):
 // lane l accumulates, in increasing j then e order, the elements d = (j*32 + l)*8 + e
-// (e = 0..7) with acc = fma(a, b, acc) — the bf16 x bf16 product is exact in fp64, so this is
+// (e = 0..7) with acc = acc + a*b — the bf16 x bf16 product is exact (even in fp32), so this is
 // one rounding per addition — and the 32 partials are combined by the xor butterfly
 // 16, 8, 4, 2, 1 (p = p + p_partner).
 __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restrict__ qrow,  // smem or global
@@ -434,10 +434,13 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
-          const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
-          acc = fma(q0, e0, acc);
-          acc = fma(q1, e1, acc);
+          // bf16 x bf16 is exact in fp32 (8 + 8 significand bits), so the fp32 product converted to
+          // fp64 equals the exact product: one F2F per element instead of two (the fp32->fp64
+          // conversion pipe, not HBM, was the limiter of this kernel)
+          const float p0 = __uint_as_float(qw[w] << 16) * __uint_as_float(ew[w] << 16);
+          const float p1 = __uint_as_float(qw[w] & 0xFFFF0000u) * __uint_as_float(ew[w] & 0xFFFF0000u);
+          acc += (double)p0;
+          acc += (double)p1;
         }
       }
     }
@@ -449,10 +452,10 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
       const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const double e0 = (double)__uint_as_float(ew[w] << 16), e1 = (double)__uint_as_float(ew[w] & 0xFFFF0000u);
-        const double q0 = (double)__uint_as_float(qw[w] << 16), q1 = (double)__uint_as_float(qw[w] & 0xFFFF0000u);
-        acc = fma(q0, e0, acc);
-        acc = fma(q1, e1, acc);
+        const float p0 = __uint_as_float(qw[w] << 16) * __uint_as_float(ew[w] << 16);
+        const float p1 = __uint_as_float(qw[w] & 0xFFFF0000u) * __uint_as_float(ew[w] & 0xFFFF0000u);
+        acc += (double)p0;
+        acc += (double)p1;
       }
     }
   }
