@@ -303,13 +303,33 @@ class Corpus:
                     mask[i] = True
         return mask
 
+    def _import_mask_words(self, path: str) -> np.ndarray:
+        """Packed bitmask of the premises `path` imports (transitively); cached per file, like the
+        reference's `imported_premises_cache` (common.py:265-278)."""
+        cache = self.__dict__.setdefault("_import_words_cache", {})
+        words = cache.get(path)
+        if words is None or len(words) != (len(self.all_premises) + 31) // 32:
+            mask = np.zeros((len(self.all_premises) + 31) // 32 * 32, dtype=bool)
+            for dep in self._deps[path]:
+                a, b = self._range[dep]
+                mask[a:b] = True
+            words = np.packbits(mask.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view("<u4").copy()
+            cache[path] = words
+        return words
+
     def accessible_mask_words(self, path: str, pos: Any) -> np.ndarray:
-        """`accessible_mask` packed little-endian into uint32 words (bit i&31 of word i>>5)."""
-        mask = self.accessible_mask(path, pos)
-        n_words = (len(mask) + 31) // 32
-        padded = np.zeros(n_words * 32, dtype=bool)
-        padded[: len(mask)] = mask
-        return np.packbits(padded.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view("<u4").copy()
+        """`accessible_mask` packed little-endian into uint32 words (bit i&31 of word i>>5).
+        Per query only the own-file prefix is recomputed; the imports part comes from a per-file cache."""
+        pos = Pos.from_any(pos)
+        words = self._import_mask_words(path).copy()
+        lo, hi = self._range[path]
+        own = self.all_premises[lo:hi]
+        visible_names = {p.full_name for p in own if p.end <= pos}
+        if visible_names:
+            for i, p in enumerate(own, start=lo):
+                if p.full_name in visible_names:
+                    words[i >> 5] |= np.uint32(1 << (i & 31))
+        return words
 
     # ---- nearest-neighbour search (signature of reference common.py:299-305) ---------------
     def get_nearest_premises(self, premise_embeddings, batch_context: List[Context], batch_context_emb, k: int):

@@ -72,8 +72,14 @@ class B200PremiseRetriever:
             self.corpus_embeddings = None
             self.embeddings_staled = True
         else:
-            with open(path, "rb") as fh:
-                indexed = pickle.load(fh)
+            try:
+                with open(path, "rb") as fh:
+                    indexed = pickle.load(fh)
+            except (ModuleNotFoundError, AttributeError):
+                # an index written by the reference itself (classes from `common` / `lean_dojo`)
+                from .compat import load_reference_index
+
+                indexed = load_reference_index(path)
             self.corpus = indexed.corpus
             self.corpus_embeddings = indexed.embeddings
             self.embeddings_staled = False

@@ -174,3 +174,73 @@ def test_shard_bounds_partition_rows():
         assert b[0] == 0 and b[-1] == n and len(b) == w + 1
         sizes = np.diff(b)
         assert (sizes >= 0).all() and sizes.max() - sizes.min() <= 1
+
+
+# ------------------------------------------------------------------------------- metrics / compat
+def test_recall_and_mrr_matches_reference_arithmetic():
+    from reprover_b200.evaluation import recall_and_mrr
+
+    P = [Premise("A.lean", f"p{i}", Pos(i + 1, 0), Pos(i + 1, 1), "c") for i in range(6)]
+    retrieved = [[P[0], P[1], P[2]], [P[3], P[4], P[5]], [P[0], P[2], P[4]]]
+    positives = [[P[1], P[5]], [], [P[5]]]
+    recall, mrr, n = recall_and_mrr(positives, retrieved, 3)
+    # example 0: hits after j=1,2,3 -> 0, 1, 1 of 2 positives; example 1 skipped; example 2: no hit
+    assert n == 2
+    assert recall == pytest.approx([0.0, 25.0, 25.0])
+    assert mrr == pytest.approx((0.5 + 0.0) / 2)
+
+
+def test_reference_index_pickle_is_readable(tmp_path):
+    """An IndexedCorpus pickled by the reference (classes `common.*`, `lean_dojo.Pos`, networkx graph)
+    loads through reprover_b200.compat without either module being importable."""
+    import subprocess
+    import sys
+    import textwrap
+
+    out = tmp_path / "ref_index.pickle"
+    script = textwrap.dedent(f"""
+        import pickle, sys, types
+        from dataclasses import dataclass, field
+        import networkx as nx, torch
+        ld = types.ModuleType("lean_dojo"); sys.modules["lean_dojo"] = ld
+        common = types.ModuleType("common"); sys.modules["common"] = common
+        @dataclass(frozen=True, order=True)
+        class Pos:
+            line_nb: int
+            column_nb: int
+        Pos.__module__ = "lean_dojo"; ld.Pos = Pos
+        @dataclass(unsafe_hash=True)
+        class Premise:
+            path: str
+            full_name: str
+            start: Pos = field(repr=False)
+            end: Pos = field(repr=False, compare=False)
+            code: str = field(compare=False)
+        @dataclass(frozen=True)
+        class File:
+            path: str
+            premises: list = field(repr=False, compare=False)
+        class Corpus:
+            pass
+        @dataclass(frozen=True)
+        class IndexedCorpus:
+            corpus: Corpus
+            embeddings: torch.Tensor
+        for c in (Premise, File, Corpus, IndexedCorpus):
+            c.__module__ = "common"; setattr(common, c.__name__, c)
+        fa = File("A.lean", [Premise("A.lean", "A.x", Pos(1, 0), Pos(2, 0), "def x := 1")])
+        fb = File("B.lean", [Premise("B.lean", "B.y", Pos(3, 0), Pos(4, 0), "def y := 2"),
+                             Premise("B.lean", "B.z", Pos(5, 0), Pos(6, 0), "def z := 3")])
+        g = nx.DiGraph(); g.add_node("A.lean", file=fa); g.add_node("B.lean", file=fb); g.add_edge("B.lean", "A.lean")
+        corpus = Corpus(); corpus.transitive_dep_graph = nx.transitive_closure_dag(g)
+        corpus.all_premises = fa.premises + fb.premises; corpus.imported_premises_cache = {{}}
+        pickle.dump(IndexedCorpus(corpus, torch.arange(12.).reshape(3, 4)), open(r"{out}", "wb"))
+    """)
+    subprocess.run([sys.executable, "-c", script], check=True)
+    from reprover_b200.compat import load_reference_index
+
+    idx = load_reference_index(str(out))
+    assert [p.full_name for p in idx.corpus.all_premises] == ["A.x", "B.y", "B.z"]
+    assert idx.corpus.get_dependencies("B.lean") == ["A.lean"] and idx.embeddings.shape == (3, 4)
+    assert idx.corpus.accessible_mask("B.lean", Pos(4, 5)).tolist() == [True, True, False]
+    assert idx.corpus.all_premises[1].end == Pos(4, 0)

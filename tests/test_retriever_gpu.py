@@ -154,3 +154,31 @@ def test_fp32_embedding_dtype_option(setup, cuda_device):
     assert e.dtype == torch.float32 and abs(float(e.norm()) - 1.0) < 1e-5
     with pytest.raises(NotImplementedError):
         B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=torch.float16)
+
+
+def test_validation_and_predict_steps(setup):
+    """The batched validate / predict path (reference retrieval/model.py:215-327) on top of the engine."""
+    from reprover_b200.evaluation import predict_step, recall_and_mrr, validation_step
+
+    r = setup["retr"]
+    old_k = r.num_retrieved
+    r.num_retrieved = 10
+    try:
+        sdat, soff = synth.synth_states(4, seed=91, min_len=12, max_len=100)
+        states = [s.decode() for s in synth.split_strings(sdat, soff)]
+        ctxs = [Context("Synth/F3.lean", "t", Pos(400, 0), s) for s in states]
+        premises, _ = r.retrieve_batch(states, ["Synth/F3.lean"] * 4, ["t"] * 4, [Pos(400, 0)] * 4, 10)
+        positives = [[premises[0][0], premises[0][4]], [], [premises[2][9]], [r.corpus.all_premises[-1]]]
+        batch = {"context": ctxs, "all_pos_premises": positives, "url": ["u"] * 4, "commit": ["c"] * 4,
+                 "file_path": ["Synth/F3.lean"] * 4, "full_name": ["t"] * 4, "start": [Pos(400, 0)] * 4,
+                 "tactic_idx": list(range(4))}
+        m = validation_step(r, batch)
+        want_recall, want_mrr, n = recall_and_mrr(positives, premises, 10)
+        assert n == 3 and m["MRR"] == pytest.approx(want_mrr) and m["Recall@10_val"] == pytest.approx(want_recall[9])
+        assert m["Recall@1_val"] == pytest.approx(100.0 * (0.5 + 0.0 + 0.0) / 3)
+        recs = predict_step(r, batch)
+        assert len(recs) == 4 and recs[2]["tactic_idx"] == 2
+        assert [p.full_name for p in recs[0]["retrieved_premises"]] == [p.full_name for p in premises[0]]
+        assert len(recs[0]["scores"]) == 10
+    finally:
+        r.num_retrieved = old_k
