@@ -188,6 +188,11 @@ class Corpus:
                     data = json.loads(line)
                     self._add_file(File.from_data(data), data["imports"])
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_import_words_cache", None)  # derived data: keep index pickles lean
+        return state
+
     @classmethod
     def from_files(cls, files: Iterable[Tuple[File, Iterable[str]]]) -> "Corpus":
         c = cls()
