@@ -218,8 +218,13 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           uint32_t v[32];
           tmem_ld_32x32(tmem_S + lane_addr, v);
           tmem_ld_wait();
+          if (kb + 32 <= len) {  // CTA-uniform: only a partial chunk needs the key mask
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s0[j] = (kb + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+            for (int j = 0; j < 32; ++j) s0[j] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s0[j] = (kb + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+          }
           add_bias32(s0, sBias, kb - qpos + R, R);
         }
         const bool second = kb + 32 < len;  // CTA-uniform
@@ -227,19 +232,32 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           uint32_t v[32];
           tmem_ld_32x32(tmem_S + lane_addr + 32, v);
           tmem_ld_wait();
+          if (kb + 64 <= len) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s1[j] = (kb + 32 + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+            for (int j = 0; j < 32; ++j) s1[j] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s1[j] = (kb + 32 + j < len) ? __uint_as_float(v[j]) : -INFINITY;
+          }
           add_bias32(s1, sBias, kb + 32 - qpos + R, R);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) s1[j] = -INFINITY;
         }
-        float m_new = m_run;
+        // row max with four independent chains (a single 64-long FMNMX chain is pure latency)
+        float mx0 = fmaxf(s0[0], s1[0]), mx1 = fmaxf(s0[1], s1[1]), mx2 = fmaxf(s0[2], s1[2]),
+              mx3 = fmaxf(s0[3], s1[3]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m_new = fmaxf(m_new, fmaxf(s0[j], s1[j]));
+        for (int j = 4; j < 32; j += 4) {
+          mx0 = fmaxf(mx0, fmaxf(s0[j], s1[j]));
+          mx1 = fmaxf(mx1, fmaxf(s0[j + 1], s1[j + 1]));
+          mx2 = fmaxf(mx2, fmaxf(s0[j + 2], s1[j + 2]));
+          mx3 = fmaxf(mx3, fmaxf(s0[j + 3], s1[j + 3]));
+        }
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
         const float mb = m_new * kLog2e;
         scale = fast_exp2((m_run - m_new) * kLog2e);  // 0 on the first step (m_run = -inf)
-        float l_add = 0.f;
+        float la0 = 0.f, la1 = 0.f;  // two independent sum chains
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];
@@ -247,7 +265,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           for (int j = 0; j < 32; j += 2) {
             const float p0 = fast_exp2(fmaf(h ? s1[j] : s0[j], kLog2e, -mb));
             const float p1 = fast_exp2(fmaf(h ? s1[j + 1] : s0[j + 1], kLog2e, -mb));
-            l_add += p0 + p1;
+            la0 += p0;
+            la1 += p1;
             pk[j >> 1] = pack_bf16x2(p0, p1);
           }
           // keys [32h, 32h+32) = 16-byte slots 4h..4h+3 of this row's 128-byte line
@@ -258,6 +277,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
           }
         }
+        const float l_add = la0 + la1;
         m_run = m_new;
         l_run = l_run * scale + l_add;
       } else {
