@@ -13,12 +13,13 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--skip-encode", action="store_true")
 ap.add_argument("--skip-retrieve", action="store_true")
 ap.add_argument("--tag", default="quick")
+ap.add_argument("--max-tokens", type=int, default=1 << 18)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 out = {}
 if not args.skip_encode:
     cfg = dict(synth.BYT5_SMALL)
-    eng = T5EncoderEngine(cfg, synth.random_t5_state_dict(cfg, seed=synth.SEED), dev)
+    eng = T5EncoderEngine(cfg, synth.random_t5_state_dict(cfg, seed=synth.SEED), dev, max_tokens_per_call=args.max_tokens)
     data, offsets = synth.synth_premises(args.premises, seed=synth.SEED)
     tl = np.minimum(np.diff(offsets) + 1, 512).astype(np.float64)
     flops = float((tl * (434_110_464.0 + 18_432.0 * tl)).sum())
