@@ -26,6 +26,14 @@ namespace rpx {
 namespace {
 
 constexpr int kSimBlockN = 256;
+#ifndef RPX_SIM_SAMPLE_TILES
+#define RPX_SIM_SAMPLE_TILES 32
+#endif
+#ifndef RPX_SIM_SEL_SLACK
+#define RPX_SIM_SEL_SLACK 16
+#endif
+constexpr int kSampleTiles = RPX_SIM_SAMPLE_TILES;  // 32 x 256 = 8192 sampled premises
+constexpr int kSelSlack = RPX_SIM_SEL_SLACK;        // stage 2 re-scores between n_res and n_res + kSelSlack rows
 constexpr unsigned kFull = 0xffffffffu;
 
 // Monotone map float bits -> uint32 (a > b  <=>  fkey(a) > fkey(b), -0 < +0).
@@ -548,11 +556,11 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
 
   // ---- threshold: count(key >= lo) in [n_res, n_res + 16] (keys are distinct, so it exists)
   uint64_t lo = kmin;
-  if (total > n_res + 16) {
+  if (total > n_res + kSelSlack) {
     uint64_t hi = kmax;  // count(>= kmax) = 1 < n_res
     int count_lo = total;
     // invariant: count(>= lo) = count_lo >= n_res, count(>= hi) < n_res
-    for (int iter = 0; count_lo > n_res + 16 && hi - lo > 1; ++iter) {
+    for (int iter = 0; count_lo > n_res + kSelSlack && hi - lo > 1; ++iter) {
       const uint64_t mid = lo + (hi - lo) / 2;
       int m = 0;
       for (int i = tid; i < total; i += kSelThreads) m += keys[i] >= mid ? 1 : 0;
@@ -709,8 +717,8 @@ int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
   pl->cand_bytes = align_up((size_t)pl->grid * kBlockM * pl->cap * sizeof(uint2), 256);
   pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);
   pl->gthr_bytes = align_up((size_t)pl->tiles_m * kBlockM * sizeof(uint32_t), 256);
-  // sampling pass: up to 32 tiles (8192 premises), score matrix capped at 64 MB
-  pl->sample_tiles = 32;
+  // sampling pass: up to kSampleTiles tiles of 256 premises, score matrix capped at 64 MB
+  pl->sample_tiles = kSampleTiles;
   while (pl->sample_tiles > 4 &&
          (size_t)pl->tiles_m * kBlockM * pl->sample_tiles * kSimBlockN * sizeof(float) > (size_t)64 << 20)
     pl->sample_tiles /= 2;

@@ -154,3 +154,15 @@ def test_full_size_cfg3_properties(rpx_lib, cuda_device):
         gap = (top.values[:, k - 1] - top.values[:, k]).abs()
         assert (same | (gap < 1e-12)).all()
         del S
+
+
+def test_more_queries_than_one_launch_covers(rpx_lib, cuda_device):
+    """nq > 128 * #SMs: the query set is processed in several launches (one CTA per query block,
+    no cross-CTA list merging) — results must not depend on the split."""
+    n_sms = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    nq = 128 * n_sms + 257
+    _check(_unit(nq, 64, 41, cuda_device), _unit(3001, 64, 42, cuda_device), 5)
+
+
+def test_odd_number_of_query_blocks(rpx_lib, cuda_device):
+    _check(_unit(3 * 128 + 5, 128, 43, cuda_device), _unit(70_000, 128, 44, cuda_device), 100)
