@@ -76,6 +76,7 @@ struct TileCtx {
   int m_blk, n_blk;
   int M, N;
   int next_m0, next_n0;  // origin of the next tile this CTA will process (next_m0 < 0: none)
+  int next_cols;         // its width
   int part, split;       // this warp handles the 32-column chunks with (chunk % split) == part
 };
 
@@ -250,9 +251,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (nt < num_tiles) {
           t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * kBlockM;
           t.next_n0 = (M_FASTEST ? nt / tiles_m : nt % tiles_n) * BLOCK_N;
+          t.next_cols = N - t.next_n0 < BLOCK_N ? N - t.next_n0 : BLOCK_N;
         } else {
           t.next_m0 = -1;
           t.next_n0 = 0;
+          t.next_cols = 0;
         }
       }
       epi.before_wait(t);
@@ -404,7 +407,7 @@ struct EpiResidual {
     const int m = t.next_m0 + grp * 32 + lane;
     if (m < t.M) {
       const float* rowp = p.h32 + (size_t)m * p.ld + t.next_n0;
-      const int n_cols = t.N - t.next_n0 < 256 ? t.N - t.next_n0 : 256;
+      const int n_cols = t.next_cols;
       for (int c = 32 * t.part; c < n_cols; c += 32 * t.split)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + c));
     }

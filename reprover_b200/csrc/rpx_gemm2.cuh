@@ -102,6 +102,29 @@ struct Gemm2Cfg {
   }
 };
 
+// Column range of n-tile `n_blk`: N is cut into tiles_n near-equal tiles in units of 32 columns
+// (the wider ones last) instead of tiles_n - 1 full tiles and a short tail.  With N = 1472 the
+// tail tile would be 192 wide: the pairs that visit it (tile = pair + i * n_pairs walks a fixed
+// residue class of n_blk) ran ~8 % ahead of the others, the six pairs sharing an A row block fell
+// out of step and A came from DRAM ~3x instead of once (ncu: 7.1 GB read for the FFN
+// down-projection against 3.4 GB algorithmic).  224/224/256/256/256/256 gives every pair the same
+// work per three tiles.
+#ifndef RPX_GEMM2_EVEN_SPLIT
+#define RPX_GEMM2_EVEN_SPLIT 1  // 0: full tiles + short tail (kept for A/B runs)
+#endif
+__device__ __forceinline__ void n_tile_range(int n_blk, int N, int tiles_n, int& n0, int& n_this) {
+#if !RPX_GEMM2_EVEN_SPLIT
+  n0 = n_blk * 256;
+  n_this = N - n0 > 256 ? 256 : ((N - n0 + 31) & ~31);
+  return;
+#endif
+  const int units = (N + 31) >> 5;
+  const int base = units / tiles_n;
+  const int first_wide = tiles_n - (units - base * tiles_n);
+  n0 = 32 * (n_blk * base + (n_blk > first_wide ? n_blk - first_wide : 0));
+  n_this = 32 * (base + (n_blk >= first_wide ? 1 : 0));
+}
+
 template <int STAGES, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -161,11 +184,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
         const int n_blk = tile % tiles_n;
         const int m_blk = tile / tiles_n;
-        int n_this = N - n_blk * BLOCK_N;
-        if (n_this > BLOCK_N) n_this = BLOCK_N;
-        n_this = (n_this + 31) & ~31;
+        int n0, n_this;
+        n_tile_range(n_blk, N, tiles_n, n0, n_this);
         const int a_row = m_blk * kPairM + (int)rank * kBlockM;
-        const int b_row = n_blk * BLOCK_N + (int)rank * (n_this / 2);
+        const int b_row = n0 + (int)rank * (n_this / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
@@ -186,10 +208,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int n_blk = tile % tiles_n;
-        int n_this = N - n_blk * BLOCK_N;
-        if (n_this > BLOCK_N) n_this = BLOCK_N;
-        n_this = (n_this + 31) & ~31;
+        int n0, n_this;
+        n_tile_range(tile % tiles_n, N, tiles_n, n0, n_this);
         const uint32_t idesc = make_idesc_bf16(kPairM, (uint32_t)n_this);
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
@@ -226,10 +246,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       t.n_blk = tile % tiles_n;
       t.m_blk = tile / tiles_n;
       t.m0 = t.m_blk * kPairM + (int)rank * kBlockM;
-      t.n0 = t.n_blk * BLOCK_N;
-      int n_this = N - t.n0;
-      if (n_this > BLOCK_N) n_this = BLOCK_N;
-      t.n_cols = n_this;
+      int n_this;
+      n_tile_range(t.n_blk, N, tiles_n, t.n0, n_this);
+      t.n_cols = n_this < N - t.n0 ? n_this : N - t.n0;
       t.row = row;
       t.part = part;
       t.split = Epi::kWarps / 4;
@@ -240,10 +259,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nt = tile + n_pairs;
         if (nt < num_tiles) {
           t.next_m0 = (nt / tiles_n) * kPairM + (int)rank * kBlockM;
-          t.next_n0 = (nt % tiles_n) * BLOCK_N;
+          n_tile_range(nt % tiles_n, N, tiles_n, t.next_n0, t.next_cols);
+          if (t.next_cols > N - t.next_n0) t.next_cols = N - t.next_n0;
         } else {
           t.next_m0 = -1;
           t.next_n0 = 0;
+          t.next_cols = 0;
         }
       }
       epi.before_wait(t);
