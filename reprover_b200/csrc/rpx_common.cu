@@ -56,6 +56,36 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
   return RPX_OK;
 }
 
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+  auto encode = resolve_encode();
+  RPX_REQUIRE(encode != nullptr, RPX_ERR_CUDA, "cuTensorMapEncodeTiled not available from driver");
+  RPX_REQUIRE(elem_bytes == 2 || elem_bytes == 4, RPX_ERR_INVALID, "TMA map: element size %d", elem_bytes);
+  RPX_REQUIRE((reinterpret_cast<uintptr_t>(gptr) & 15) == 0, RPX_ERR_INVALID,
+              "TMA operand base must be 16-byte aligned");
+  RPX_REQUIRE((ld_elems * elem_bytes) % 16 == 0, RPX_ERR_INVALID, "TMA row pitch must be a multiple of 16 bytes");
+  RPX_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols >= 1 && box_cols <= 256, RPX_ERR_INVALID,
+              "TMA box out of range");
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else RPX_REQUIRE(swizzle_bytes == 0, RPX_ERR_INVALID, "TMA map: swizzle span %d", swizzle_bytes);
+  RPX_REQUIRE(swizzle_bytes == 0 || (int)(box_cols * elem_bytes) <= swizzle_bytes, RPX_ERR_INVALID,
+              "TMA map: inner box extent exceeds the swizzle span");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                      const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RPX_REQUIRE(r == CUDA_SUCCESS, RPX_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows);
+  return RPX_OK;
+}
+
 int get_device_info(DeviceInfo* out) {
   static std::mutex mu;
   static DeviceInfo cache[64];

@@ -47,6 +47,11 @@ const char* get_error();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows);
 
+// General 2-D row-major map: `elem_bytes` 2 (bf16) or 4 (fp32), box {box_cols, box_rows}, swizzle span
+// `swizzle_bytes` in {0, 32, 64, 128} (box_cols * elem_bytes must not exceed it when non-zero).
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+
 struct DeviceInfo {
   int device = -1;
   int num_sms = 0;

@@ -43,6 +43,69 @@ int encoder_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, 
 #endif
 }
 
+// Residual-update GEMMs (attention output projection, FFN down projection).  With the 2-CTA kernel
+// the residual stream moves through TMA (EpiResidualTma: RPX_RES_RING boxes per warp, which leaves
+// room for RPX_RES_STAGES operand stages); -DRPX_RES_TMA=0 or a model too narrow for the ring's
+// look-ahead uses the register epilogue.
+#ifndef RPX_RES_TMA
+#define RPX_RES_TMA (RPX_GEMM_2CTA && RPX_EPI_WARPS == 4)
+#endif
+// The TMA epilogue pays for its ring with operand stages (4 instead of 6), which costs a
+// tensor-bound GEMM more than the epilogue gains: it is used while the MMA time of a tile
+// (~0.43 us per 64 of K) is below the ~7 us the tile's 320 KB of residual traffic need, i.e. for
+// the attention output projection (K = 384: 57.6 -> 38.5 ms per 4096-premise step) but not for the
+// FFN down projection (K = 3584: 99.8 ms with the register epilogue, 114 ms with this one).
+#ifndef RPX_RES_TMA_MAX_K
+#define RPX_RES_TMA_MAX_K 1024
+#endif
+#ifndef RPX_RES_RING
+#define RPX_RES_RING 4
+#endif
+#ifndef RPX_RES_STAGES
+#define RPX_RES_STAGES 4
+#endif
+using EpiResTma = EpiResidualTma<RPX_RES_RING>;
+
+struct ResidualMaps {
+  bool use_tma = false;
+  CUtensorMap h32, h16;
+};
+
+// Narrowest n-tile of the 2-CTA kernel for an N-column output (see n_tile_range).
+inline int min_tile_cols(int N) {
+  const int tiles_n = ceil_div(N, kBlockN);
+  return 32 * (ceil_div(N, 32) / tiles_n);
+}
+
+int make_residual_maps(ResidualMaps* m, float* h32, __nv_bfloat16* h16, int T, int D) {
+  m->use_tma = false;
+#if RPX_RES_TMA
+  if (D % 32 == 0 && min_tile_cols(D) >= 32 * (RPX_RES_RING - 1)) {
+    RPX_TRY(make_tmap_2d(&m->h32, 4, h32, (uint64_t)T, (uint64_t)D, (uint64_t)D, 32, 32, 128));
+    RPX_TRY(make_tmap_2d(&m->h16, 2, h16, (uint64_t)T, (uint64_t)D, (uint64_t)D, 32, 32, 64));
+    m->use_tma = true;
+  }
+#endif
+  return RPX_OK;
+}
+
+// h32 += A @ B^T, h16 = bf16(h32), ss = partial sums of h32^2 per n-tile.
+int residual_gemm(const ResidualMaps& maps, const void* A, int64_t lda, const void* B, int64_t ldb, int T, int D,
+                  int K, float* h32, __nv_bfloat16* h16, float* ss, cudaStream_t st) {
+#if RPX_RES_TMA
+  if (maps.use_tma && K <= RPX_RES_TMA_MAX_K) {
+    EpiResTma::Params ep;
+    ep.tm_h32 = maps.h32;
+    ep.tm_h16 = maps.h16;
+    ep.ss_out = ss;
+    ep.ss_stride = T;
+    return launch_gemm2<EpiResTma, RPX_RES_STAGES>(A, lda, B, ldb, T, D, K, ep, st);
+  }
+#endif
+  EpiResidual::Params ep{h32, h16, D, ss, T};
+  return encoder_gemm<EpiResidual>(A, lda, B, ldb, T, D, K, ep, st);
+}
+
 struct LayerW {
   const __nv_bfloat16* qkv;  // [3*inner, D]   (ln0 folded)
   const __nv_bfloat16* o;    // [D, inner]
@@ -237,6 +300,8 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     return RPX_OK;
   };
   RPX_TRY(dump(0));
+  ResidualMaps maps;
+  RPX_TRY(make_residual_maps(&maps, ws.h32, ws.h16, T, D));
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& w = e->layers[l];
     {
@@ -251,8 +316,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     }
     {
       Prof p(e, st, 3);
-      EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
-      RPX_TRY((encoder_gemm<EpiResidual>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+      RPX_TRY(residual_gemm(maps, ws.attn, inner, w.o, inner, T, D, inner, ws.h32, ws.h16, ws.ssB, st));
     }
     {
       Prof p(e, st, 4);
@@ -261,8 +325,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
     }
     {
       Prof p(e, st, 5);
-      EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
-      RPX_TRY((encoder_gemm<EpiResidual>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+      RPX_TRY(residual_gemm(maps, ws.ffn, F, w.wo, F, T, D, F, ws.h32, ws.h16, ws.ssA, st));
     }
     RPX_TRY(dump(l + 1));
   }

@@ -489,6 +489,125 @@ struct EpiResidual {
   __device__ void finish() {}
 };
 
+// The same residual update with the data movement handed to the TMA engine (2-CTA kernel only).
+//
+// Why: with K = 384 (attention output projection) the MMA of a tile takes ~2 us while its
+// epilogue has to move 320 KB per CTA; four warps issuing their own loads keep only ~16 KB in
+// flight per SM, and ncu's stall samples sat on the first use of the looked-ahead residual
+// registers (the kernel ran at ~3.2 TB/s inside the step).  Here each epilogue warp owns a ring
+// of R 32x32 fp32 boxes in shared memory: one lane keeps R-1 box loads in flight (across tile
+// boundaries — the next tile's coordinates are known), the warp updates a box in place, row per
+// thread (TMEM lane == thread == box row, 128-byte swizzle => conflict-free 16-byte accesses),
+// and the fp32 box plus its bf16 copy leave again as two bulk tensor stores.  No thread ever
+// waits on a global load or store; rows past M are zero-filled on load and clipped on store.
+template <int R>
+struct EpiResidualTma {
+  struct alignas(64) Params {
+    CUtensorMap tm_h32;  // fp32 [M, N], box 32 cols x 32 rows, 128-byte swizzle (load + store)
+    CUtensorMap tm_h16;  // bf16 [M, N], box 32 cols x 32 rows,  64-byte swizzle (store)
+    float* ss_out;       // [tiles_n][ss_stride]
+    int ss_stride;
+  };
+  static constexpr int kWarps = 4;
+  static constexpr int kInBytes = 32 * 32 * 4;
+  static constexpr int kOutBytes = 32 * 32 * 2;
+  static constexpr int kWarpBytes = R * kInBytes + 2 * kOutBytes;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kWarps * kWarpBytes + 256;
+  const Params* pp;
+  uint8_t* in;     // this warp's ring
+  uint8_t* out16;  // this warp's two bf16 staging boxes
+  uint64_t* full;  // this warp's R "box landed" barriers
+  int lane, grp;
+  uint32_t seq = 0;  // boxes consumed so far (ring slot = seq % R, parity = (seq / R) & 1)
+  bool primed = false;
+
+  __device__ EpiResidualTma(const Params& p_, uint8_t* smem_extra, int row, int /*part*/) : pp(&p_) {
+    lane = row & 31;
+    grp = row >> 5;
+    uint8_t* base = smem_extra + ((1024 - (smem_u32(smem_extra) & 1023)) & 1023);
+    in = base + grp * kWarpBytes;
+    out16 = in + R * kInBytes;
+    full = reinterpret_cast<uint64_t*>(base + kWarps * kWarpBytes) + grp * R;
+    if (lane == 0) {
+      for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  // Box `idx` counted from the first box of tile t (running on into the next tile) -> ring.
+  __device__ __forceinline__ void issue_load(const TileCtx& t, int idx, uint32_t s) const {
+    const int nch = t.n_cols >> 5;
+    int c0, c1;
+    if (idx < nch) {
+      c0 = t.n0 + 32 * idx;
+      c1 = t.m0 + grp * 32;
+    } else {
+      idx -= nch;
+      if (t.next_m0 < 0 || idx >= (t.next_cols >> 5)) return;
+      c0 = t.next_n0 + 32 * idx;
+      c1 = t.next_m0 + grp * 32;
+    }
+    uint64_t* bar = &full[s % R];
+    mbar_arrive_expect_tx(bar, kInBytes);
+    tma_load_2d(in + (s % R) * kInBytes, &pp->tm_h32, bar, c0, c1);
+  }
+  __device__ void before_wait(const TileCtx& t) {
+    if (primed) return;
+    primed = true;
+    if (lane == 0)
+      for (int k = 0; k < R - 1; ++k) issue_load(t, k, seq + k);
+  }
+  __device__ void tile(const TileCtx& t) {
+    const int nch = t.n_cols >> 5;
+    const int m_w = t.m0 + grp * 32;
+    const int sw = lane & 7;
+    float ss = 0.f;
+    for (int ci = 0; ci < nch; ++ci, ++seq) {
+      const uint32_t slot = seq % R;
+      mbar_wait<0>(&full[slot], (seq / R) & 1, 7);
+      uint32_t v[32];
+      tmem_ld_32x32(t.tmem + 32 * ci, v);
+      tmem_ld_wait();
+      float4* hrow = reinterpret_cast<float4*>(in + slot * kInBytes) + lane * 8;
+      uint4* orow = reinterpret_cast<uint4*>(out16 + (seq & 1) * kOutBytes) + lane * 4;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = hrow[j ^ sw];
+        x.x += __uint_as_float(v[4 * j]);
+        x.y += __uint_as_float(v[4 * j + 1]);
+        x.z += __uint_as_float(v[4 * j + 2]);
+        x.w += __uint_as_float(v[4 * j + 3]);
+        ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        hrow[j ^ sw] = x;
+        pk[2 * j] = pack_bf16x2(x.x, x.y);
+        pk[2 * j + 1] = pack_bf16x2(x.z, x.w);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        orow[q ^ ((lane >> 1) & 3)] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&pp->tm_h32, in + slot * kInBytes, t.n0 + 32 * ci, m_w);
+        tma_store_2d(&pp->tm_h16, out16 + (seq & 1) * kOutBytes, t.n0 + 32 * ci, m_w);
+        bulk_commit_group();
+        // the previous box's stores have drained their shared-memory reads: its ring slot takes the
+        // load R-1 boxes ahead, and its bf16 staging box is free for the next iteration
+        bulk_wait_group_read<1>();
+        issue_load(t, ci + R - 1, seq + R - 1);
+      }
+      __syncwarp();
+    }
+    const int m = m_w + lane;
+    if (m < t.M) pp->ss_out[(size_t)t.n_blk * pp->ss_stride + m] = ss;
+  }
+  __device__ void finish() {
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
+  }
+};
+
 // gelu_new (tanh form) — HF activations.py NewGELUActivation, used by T5 "gated-gelu".
 __device__ __forceinline__ float gelu_new(float x) {
   const float k0 = 0.7978845608028654f;  // sqrt(2/pi)

@@ -128,7 +128,7 @@ __device__ __forceinline__ void n_tile_range(int n_blk, int N, int tiles_n, int&
 template <int STAGES, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                int tiles_m, int tiles_n, typename Epi::Params ep) {
+                int tiles_m, int tiles_n, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = Gemm2Cfg<STAGES>;
   constexpr int BLOCK_N = Cfg::kBlockN;
   extern __shared__ uint8_t smem_raw[];

@@ -47,10 +47,10 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
 constexpr int kGemm2Stages = 6;
 
 // 2-CTA (cta_group::2) launcher: 256 x 256 tiles, one CTA pair per tile, persistent over num_sms/2 pairs.
-template <class Epi>
+template <class Epi, int STAGES = kGemm2Stages>
 int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                  const typename Epi::Params& ep, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<kGemm2Stages>;
+  using Cfg = Gemm2Cfg<STAGES>;
   RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
   RPX_REQUIRE(N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
@@ -64,7 +64,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, 
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "gemm2: needs %zu B smem, device allows %zu", smem,
               dev.smem_optin);
-  auto kern = gemm_tc2_kernel<kGemm2Stages, Epi>;
+  auto kern = gemm_tc2_kernel<STAGES, Epi>;
   static thread_local int configured_dev = -1;
   if (configured_dev != dev.device) {
     RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -127,6 +127,19 @@ RPX_DEVICE void tma_load_2d_hint(void* smem_dst, const void* tmap, uint64_t* bar
         "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// 2-D tiled store shared -> global, tracked by the issuing thread's bulk async-group.
+RPX_DEVICE void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+RPX_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Until at most N of this thread's bulk groups still have shared-memory reads outstanding.
+template <int N>
+RPX_DEVICE void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 // L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking).
 RPX_DEVICE void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
