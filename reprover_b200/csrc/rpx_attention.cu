@@ -26,6 +26,12 @@ namespace rpx {
 namespace {
 
 constexpr int kHD = 64;    // head dim (d_kv)
+#ifndef RPX_ATTN_DRIVER_HINT_NS
+#define RPX_ATTN_DRIVER_HINT_NS 0
+#endif
+// Suspend hint for the driver thread's LONG waits (first Q/K tiles from DRAM, a whole softmax step
+// of the four other warps).  The short handshakes stay pure spins.
+constexpr uint32_t kDriverHintNs = RPX_ATTN_DRIVER_HINT_NS;
 constexpr int kQT = 128;   // query rows per CTA (UMMA M)
 constexpr int kKT = 64;    // keys per step (UMMA N for S, K extent for PV)
 constexpr int kAttnThreads = 160;  // 4 softmax warps + 1 warp whose elected thread drives TMA and MMA
@@ -67,21 +73,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t m, uint32_t 
   return make_idesc_bf16(m, n) | (1u << 16);
 }
 
-// s[j] += relative-position bias of key (key0 + j) for this row; LUT index clamp(d0 + j, 0, 2R).
-// Three regimes per (row, 32-key chunk): entirely clamped (one constant), entirely inside the table
-// (no clamp), or straddling an edge (per-element clamp; at most two chunks per row).
-RPX_DEVICE void add_bias32(float (&s)[32], const float* __restrict__ sBias, int d0, int R) {
-  if (d0 >= 2 * R || d0 + 31 <= 0) {
-    const float b = sBias[d0 >= 2 * R ? 2 * R : 0];
+// Relative-position bias in shared memory.  The table bias[clamp(key - query + R, 0, 2R)] is stored
+// padded with 31 copies of its edge values on either side, so the 32 consecutive keys of a chunk
+// read 32 consecutive entries starting at clamp(d0, -31, 2R) + 31 whatever the row — no per-element
+// clamp and no per-lane regime (lanes of a warp sit at consecutive d0, so any branch on it diverges).
+// Four copies, copy c shifted left by c entries, make that run 16-byte aligned for every start
+// (8 LDS.128 per chunk instead of 32 LDS.32); the copy stride is 8 mod 32 words, which spreads the
+// quarter-warp's eight loads over all 32 banks.
+__host__ __device__ constexpr int bias_padded_len(int R) { return 2 * R + 63; }
+__host__ __device__ constexpr int bias_copy_stride(int R) { return ((bias_padded_len(R) + 31) / 32) * 32 + 8; }
+
+RPX_DEVICE void add_bias32(float (&s)[32], const float* __restrict__ sBias, int d0, int R, int stride) {
+  const int a = min(max(d0, -31), 2 * R) + 31;
+  const int c = a & 3;
+  const float4* bp = reinterpret_cast<const float4*>(sBias + c * stride + (a - c));
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s[j] += b;
-  } else if (d0 >= 0 && d0 + 31 <= 2 * R) {
-    const float* bp = sBias + d0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s[j] += bp[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s[j] += sBias[min(max(d0 + j, 0), 2 * R)];
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = bp[j];
+    s[4 * j] += b.x;
+    s[4 * j + 1] += b.y;
+    s[4 * j + 2] += b.z;
+    s[4 * j + 3] += b.w;
   }
 }
 
@@ -100,7 +112,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
   float* sBias = reinterpret_cast<float*>(smem + kOffBias);
   const int lut_w = 2 * R + 1;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBias + ((lut_w * 4 + 15) & ~15));
+  const int bstride = bias_copy_stride(R);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBias + 4 * bstride * 4);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k_full = bars + 1;
   uint64_t* bar_k_free = bars + 2;
@@ -109,14 +122,18 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   uint64_t* bar_s_full = bars + 5;
   uint64_t* bar_p_ready = bars + 6;
   uint64_t* bar_o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_s_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = n_heads * kHD;
   const int n_kt = (len + kKT - 1) / kKT;
 
   if (threadIdx.x < 128)
-    for (int i = threadIdx.x; i < lut_w; i += 128) sBias[i] = bias_lut[head * lut_w + i];
+    for (int i = threadIdx.x; i < 4 * bstride; i += 128) {
+      const int c = i / bstride, k = i - c * bstride;  // copy c, entry k = padded[k + c]
+      sBias[i] = bias_lut[head * lut_w + min(max(k + c - 31, 0), 2 * R)];
+    }
   if (warp == 4) {
     if (elect_one()) {
       mbar_init(bar_q, 1);
@@ -127,6 +144,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       mbar_init(bar_s_full, 1);
       mbar_init(bar_p_ready, 128);
       mbar_init(bar_o_full, 1);
+      mbar_init(bar_s_free, 128);
       fence_mbar_init();
     }
     __syncwarp();
@@ -155,8 +173,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffK));
       const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kOffP));
       const uint32_t v_base = smem_u32(smem + kOffV);
-      mbar_wait<0>(bar_q, 0, 12);
-      mbar_wait<0>(bar_k_full, 0, 13);
+      mbar_wait<kDriverHintNs>(bar_q, 0, 12);
+      mbar_wait<kDriverHintNs>(bar_k_full, 0, 13);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
@@ -164,13 +182,24 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       umma_commit(bar_k_free);
       for (int kt = 0; kt < n_kt; ++kt) {
         const bool more = kt + 1 < n_kt;
-        if (more) {  // K(kt+1) as soon as S(kt) has read K(kt)
+        if (more) {
+          // K(kt+1) as soon as S(kt) has read K(kt)
           mbar_wait<0>(bar_k_free, kt & 1, 11);
           mbar_arrive_expect_tx(bar_k_full, kKVBytes);
           tma_load_2d(smem + kOffK, &tm_kv, bar_k_full, kcol, t0 + (kt + 1) * kKT);
+          // S(kt+1) as soon as every softmax warp holds S(kt) in registers: it is computed while they
+          // work on step kt, so the only tensor-core round trip left between two softmax steps is
+          // PV(kt), which step kt+1 needs only at its very end (P buffer, O rescale)
+          mbar_wait<kDriverHintNs>(bar_s_free, kt & 1, 21);
+          mbar_wait<0>(bar_k_full, (kt + 1) & 1, 15);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_s_full);
+          umma_commit(bar_k_free);
         }
         // O += P(kt) V(kt): needs P(kt) written (and O rescaled) and V(kt) landed
-        mbar_wait<0>(bar_p_ready, kt & 1, 14);
+        mbar_wait<kDriverHintNs>(bar_p_ready, kt & 1, 14);
         mbar_wait<0>(bar_v_full, kt & 1, 19);
         tc_fence_after();
 #pragma unroll
@@ -182,13 +211,6 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         umma_commit(bar_o_full);
         umma_commit(bar_v_free);
         if (more) {
-          // S(kt+1): the softmax warps are done with S(kt) (they signalled p_ready(kt))
-          mbar_wait<0>(bar_k_full, (kt + 1) & 1, 15);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-          umma_commit(bar_s_full);
-          umma_commit(bar_k_free);
           // V(kt+1) once PV(kt) has read V(kt)
           mbar_wait<0>(bar_v_free, kt & 1, 18);
           mbar_arrive_expect_tx(bar_v_full, kKVBytes);
@@ -203,6 +225,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const bool warp_live = q0 + warp * 32 < len;  // warp-uniform: some row of this warp is inside the sequence
     const float kLog2e = 1.4426950408889634f;
+    const float kLazyTau = 5.545177444f;  // 8 ln 2
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = smem + kOffP + row * 128;
 
@@ -210,10 +233,9 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const int kb = kt * kKT;
       mbar_wait<0>(bar_s_full, kt & 1, 16);
       tc_fence_after();
-      float scale = 1.f;
-      if (warp_live) {
-        // ---- single pass over the 64 scores of this row
+      if (warp_live) {  // warp-uniform
         float s0[32], s1[32];
+        const bool second = kb + 32 < len;  // CTA-uniform
         {
           uint32_t v[32];
           tmem_ld_32x32(tmem_S + lane_addr, v);
@@ -225,9 +247,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) s0[j] = (kb + j < len) ? __uint_as_float(v[j]) : -INFINITY;
           }
-          add_bias32(s0, sBias, kb - qpos + R, R);
         }
-        const bool second = kb + 32 < len;  // CTA-uniform
         if (second) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_S + lane_addr + 32, v);
@@ -239,11 +259,18 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) s1[j] = (kb + 32 + j < len) ? __uint_as_float(v[j]) : -INFINITY;
           }
-          add_bias32(s1, sBias, kb + 32 - qpos + R, R);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) s1[j] = -INFINITY;
         }
+        // S(kt) now lives in registers: the driver may overwrite the TMEM tile with S(kt+1), which is
+        // then computed while this step's softmax runs
+        tc_fence_before();
+        mbar_arrive(bar_s_free);
+
+        // ---- single pass over the 64 scores of this row
+        add_bias32(s0, sBias, kb - qpos + R, R, bstride);
+        if (second) add_bias32(s1, sBias, kb + 32 - qpos + R, R, bstride);
         // row max with four independent chains (a single 64-long FMNMX chain is pure latency)
         float mx0 = fmaxf(s0[0], s1[0]), mx1 = fmaxf(s0[1], s1[1]), mx2 = fmaxf(s0[2], s1[2]),
               mx3 = fmaxf(s0[3], s1[3]);
@@ -254,9 +281,21 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           mx2 = fmaxf(mx2, fmaxf(s0[j + 2], s1[j + 2]));
           mx3 = fmaxf(mx3, fmaxf(s0[j + 3], s1[j + 3]));
         }
-        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        // Lazy reference maximum: the running reference only moves when the row maximum has grown by
+        // more than kLazyTau (P <= 2^8 otherwise, harmless in bf16 / fp32), so most steps leave
+        // scale == 1 exactly and skip the O rescale below.  exp(s - m) / sum exp(s - m) does not
+        // depend on which m is used.
+        const float m_cand = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        const float m_new = (m_cand - m_run <= kLazyTau) ? m_run : m_cand;  // first step: inf > tau
         const float mb = m_new * kLog2e;
-        scale = fast_exp2((m_run - m_new) * kLog2e);  // 0 on the first step (m_run = -inf)
+        const float scale = fast_exp2((m_run - m_new) * kLog2e);  // 0 on the first step (m_run = -inf)
+        m_run = m_new;
+        // ---- PV(kt-1) has retired (it was issued a whole bias + max pass ago): the P buffer is free
+        // and O may be touched
+        if (kt > 0) {
+          mbar_wait<0>(bar_o_full, (kt - 1) & 1, 17);
+          tc_fence_after();
+        }
         float la0 = 0.f, la1 = 0.f;  // two independent sum chains
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -277,18 +316,9 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
           }
         }
-        const float l_add = la0 + la1;
-        m_run = m_new;
-        l_run = l_run * scale + l_add;
-      } else {
-#pragma unroll
-        for (int s4 = 0; s4 < 8; ++s4) *reinterpret_cast<uint4*>(prow + s4 * 16) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      // ---- O (in TMEM) *= exp(m_old - m_new) before PV(kt) accumulates onto it
-      if (kt > 0) {
-        mbar_wait<0>(bar_o_full, (kt - 1) & 1, 17);  // PV(kt-1) has retired
-        tc_fence_after();
-        if (warp_live && !__all_sync(0xffffffffu, scale == 1.f)) {
+        l_run = l_run * scale + (la0 + la1);
+        // O (in TMEM) *= exp(m_old - m_new) before PV(kt) accumulates onto it
+        if (kt > 0 && !__all_sync(0xffffffffu, scale == 1.f)) {
 #pragma unroll
           for (int c = 0; c < kHD / 32; ++c) {
             uint32_t v[32];
@@ -299,6 +329,16 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
           }
           tmem_st_wait();
+        }
+      } else {
+        // rows past the sequence: P stays zero for every step.  The o_full wait keeps this warp from
+        // running a step ahead of the others (its p_ready arrival must land in the right phase).
+        mbar_arrive(bar_s_free);
+        if (kt == 0) {
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4) *reinterpret_cast<uint4*>(prow + s4 * 16) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          mbar_wait<0>(bar_o_full, (kt - 1) & 1, 22);
         }
       }
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
@@ -355,7 +395,7 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
   CUtensorMap tm_q, tm_kv;
   RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kQT));
   RPX_TRY(make_tmap_bf16_2d(&tm_kv, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kKT));
-  const size_t smem = 1024 + kAttnSmemFixed + (((size_t)(2 * max_distance + 1) * 4 + 15) & ~(size_t)15) + 128;
+  const size_t smem = 1024 + kAttnSmemFixed + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
   RPX_REQUIRE(smem <= 100 * 1024, RPX_ERR_UNSUPPORTED, "attention: bias table too large (%zu B of shared memory)", smem);
   static thread_local int configured = -1;
   if (configured != dev.device) {
