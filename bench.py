@@ -275,12 +275,21 @@ def run_engine(args) -> dict:
         barrier(world)
         ms_r = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
         # e2e: queries from pinned host memory, results back to the host
+        res_scores = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+        res_idx = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+
+        def retrieve_host():
+            q = Q_host.to(dev, non_blocking=True)
+            r = sim_topk(q, E, k) if world == 1 else sharded_topk(q, E, k, row_offset=rank * n_idx)
+            res_scores.copy_(r[0], non_blocking=True)
+            res_idx.copy_(r[1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the caller reads the host result here
+
+        retrieve_host()   # warm-up (allocator, pinned staging)
         barrier(world)
         e0.record()
         for _ in range(reps):
-            q = Q_host.to(dev, non_blocking=True)
-            r = sim_topk(q, E, k) if world == 1 else sharded_topk(q, E, k, row_offset=rank * n_idx)
-            res = (r[0].cpu(), r[1].cpu())
+            retrieve_host()
         e1.record()
         barrier(world)
         ms_re = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps

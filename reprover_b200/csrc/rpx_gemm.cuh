@@ -376,9 +376,14 @@ struct EpiStoreBF16 {
 // 128-byte lines.  Each warp therefore transposes its 32x32 fp32 block through a swizzled
 // shared-memory tile and does the read-modify-write with lanes running along the row:
 // one instruction covers 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32).
-// Residual loads run one chunk ahead and the next tile's rows are prefetched into L2 one tile
-// ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting the chunks — was measured
+// Residual loads run one chunk ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting the chunks — was measured
 // neutral to slightly negative on B200 and is off by default.)
+// L2 prefetch of the next tile's residual rows (one tile ahead).  It paid while this epilogue also
+// served the K = 384 projection; for the tensor-bound K = 3584 one the lines are evicted again before
+// use (ncu: 6.0 GB read against 3.4 GB algorithmic), so it is off: -1.6 % on that GEMM.
+#ifndef RPX_RES_L2_PREFETCH
+#define RPX_RES_L2_PREFETCH 0
+#endif
 struct EpiResidual {
   struct Params {
     float* h32;
@@ -403,6 +408,9 @@ struct EpiResidual {
   // tile into L2 now, so that by the time they are read-modify-written (one epilogue from now)
   // the loads are L2 hits.  One 128-byte line per prefetch; row = lane.
   __device__ void before_wait(const TileCtx& t) {
+#if !RPX_RES_L2_PREFETCH
+    return;
+#endif
     if (t.next_m0 < 0) return;
     const int m = t.next_m0 + grp * 32 + lane;
     if (m < t.M) {
