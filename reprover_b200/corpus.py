@@ -18,7 +18,7 @@ import json
 import re
 from dataclasses import dataclass, field
 from functools import total_ordering
-from typing import Any, Dict, Generator, Iterable, List, Optional, Tuple
+from typing import Any, Dict, Generator, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -104,17 +104,78 @@ class Premise:
         Same rule as the reference (common.py:93-106): replace `_root_.<full_name>`;
         then, trying the fully qualified name first and successively shorter suffixes,
         wrap the first spelling (optionally «quoted») that occurs after whitespace.
-        """
+
+        Like the reference, the name is used as a regex pattern UN-escaped (its dots match any
+        character).  Compiling one or two fresh patterns per premise costs ~90 us, which would cap
+        re-indexing at ~11 k premises/s per host thread — below what one B200 encodes — so names
+        made of ordinary components (no regex metacharacter, quote or space: all but a handful of
+        Lean names) take `_sub_plain`, a direct scan with exactly `re.sub`'s semantics for that
+        pattern shape (pinned against `re.sub` in tests/test_host_cpu.py)."""
         marked = f"{MARK_START_SYMBOL}{self.full_name}{MARK_END_SYMBOL}"
         text = self.code.replace(f"_root_.{self.full_name}", marked)
         parts = self.full_name.split(".")
+        if all(_PLAIN_COMPONENT.match(c) for c in parts):
+            if parts[-1] not in text:   # every suffix ends with the last component
+                return text
+            for first in range(len(parts)):
+                replaced = _sub_plain(text, parts[first:], marked)
+                if replaced is not None:
+                    return replaced
+            return text
         for first in range(len(parts)):
             suffix = ".".join(parts[first:])
-            # NB: like the reference, the name is used as a regex pattern un-escaped.
             replaced = re.sub(f"(?<=\\s)«?{suffix}»?", marked, text)
             if replaced != text:
                 return replaced
         return text
+
+
+_PLAIN_COMPONENT = re.compile(r"[^.^$*+?{}\[\]\\|()«»\s]+\Z")
+
+
+def _sub_plain(text: str, comps: Sequence[str], repl: str) -> Optional[str]:
+    """`re.sub("(?<=\\s)«?" + ".".join(comps) + "»?", repl, text)` for metacharacter-free components
+    (so the pattern is: after whitespace, optional «, the components separated by ONE arbitrary
+    non-newline character each, optional »).  Returns None when nothing matches or the result
+    equals `text` (the caller then tries the next suffix, as the reference does)."""
+    head = comps[0]
+    out: List[str] = []
+    last = 0          # end of the previous match (text[last:] is still to be copied)
+    pos = 0
+    n = len(text)
+    while True:
+        j = text.find(head, pos)
+        if j < 0:
+            break
+        # where the match would start: at the « right before the head, else at the head itself
+        if j >= 2 and text[j - 1] == "«" and j - 1 >= last and text[j - 2].isspace():
+            start = j - 1
+        elif j >= 1 and j >= last and text[j - 1].isspace():
+            start = j
+        else:
+            pos = j + 1
+            continue
+        e = j + len(head)
+        ok = True
+        for c in comps[1:]:
+            if e >= n or text[e] == "\n" or not text.startswith(c, e + 1):
+                ok = False
+                break
+            e += 1 + len(c)
+        if not ok:
+            pos = j + 1
+            continue
+        if e < n and text[e] == "»":
+            e += 1
+        out.append(text[last:start])
+        out.append(repl)
+        last = e
+        pos = e
+    if not out:
+        return None
+    out.append(text[last:])
+    result = "".join(out)
+    return None if result == text else result
 
 
 class PremiseSet:

@@ -22,6 +22,20 @@ from .corpus import Context, Corpus, IndexedCorpus, Pos, Premise
 from .engine import T5EncoderEngine, load_hf_checkpoint
 
 
+class _Serialized:
+    """Lazy `[p.serialize() for p in premises]` (one pass, known length)."""
+
+    def __init__(self, premises: Sequence[Premise]) -> None:
+        self._premises = premises
+
+    def __len__(self) -> int:
+        return len(self._premises)
+
+    def __iter__(self):
+        for p in self._premises:
+            yield p.serialize()
+
+
 class B200PremiseRetriever:
     def __init__(self, model_name: str, lr: float = 0.0, warmup_steps: int = 0, max_seq_len: int = 2048,
                  num_retrieved: int = 100, device: Union[int, str, torch.device, None] = None,
@@ -94,38 +108,54 @@ class B200PremiseRetriever:
         return self.encoder.encode_ids(input_ids, attention_mask, out_dtype=self.dtype)
 
     @torch.no_grad()
-    def encode_texts(self, texts: Sequence[str], batch_size: int = 64, out: Optional[torch.Tensor] = None,
-                     host_chunk: int = 1024) -> torch.Tensor:
-        """tokenizer(...) + `_encode` for a list of strings (reference :199-206), rows in input order.
+    def encode_texts(self, texts: Sequence[str], batch_size: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tokenizer(...) + `_encode` for a sequence of strings (reference :199-206), rows in input order.
 
         Strings without special-token literals (practically all Lean code) go to the device as raw
         bytes; the rest are tokenised on the host with HF semantics and use the ids entry point.
-        Work is issued in chunks of `host_chunk` strings: engine calls are asynchronous, so the host
-        prepares chunk i+1 while the GPU encodes chunk i."""
+        `texts` is walked once (it may produce its strings lazily): strings are gathered until the
+        next one would overflow the engine's token budget for one call, then handed over as ONE
+        asynchronous engine call — the host gathers group i+1 while the GPU encodes group i, and every
+        call but the last is full."""
         n = len(texts)
         if out is None:
             out = torch.empty(n, self.embedding_size, dtype=self.dtype, device=self.device)
-        special: List[int] = []
-        for lo in range(0, n, host_chunk):
-            hi = min(n, lo + host_chunk)
-            chunk = texts[lo:hi]
-            odd = [i for i, t in enumerate(chunk) if "<" in t and byt5.needs_id_path(t)]
-            if not odd:
-                self.encoder.encode_strings([t.encode("utf-8") for t in chunk], self.max_seq_len,
-                                            out_dtype=self.dtype, out=out[lo:hi])
+        budget = self.encoder.max_tokens_per_call
+        special: List[Tuple[int, str]] = []
+        rows: List[int] = []
+        blobs: List[bytes] = []
+        tokens = 0
+
+        def flush() -> None:
+            nonlocal tokens
+            if not rows:
+                return
+            if rows[-1] - rows[0] + 1 == len(rows):     # contiguous: write in place
+                self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype, out=out[rows[0]:rows[-1] + 1])
+            else:
+                emb = self.encoder.encode_strings(blobs, self.max_seq_len, out_dtype=self.dtype)
+                out[torch.tensor(rows, device=self.device)] = emb
+            rows.clear()
+            blobs.clear()
+            tokens = 0
+
+        for i, t in enumerate(texts):
+            if "<" in t and byt5.needs_id_path(t):
+                special.append((i, t))
                 continue
-            special.extend(lo + i for i in odd)
-            odd_set = set(odd)
-            plain = [i for i in range(hi - lo) if i not in odd_set]
-            if plain:
-                emb = self.encoder.encode_strings([chunk[i].encode("utf-8") for i in plain], self.max_seq_len,
-                                                  out_dtype=self.dtype)
-                out[torch.tensor([lo + i for i in plain], device=self.device)] = emb
+            b = t.encode("utf-8")
+            tk = min(len(b) + 1, self.max_seq_len)
+            if tokens + tk > budget:
+                flush()
+            rows.append(i)
+            blobs.append(b)
+            tokens += tk
+        flush()
         for lo in range(0, len(special), batch_size):
-            rows = special[lo:lo + batch_size]
-            ids, mask = byt5.pad_batch([byt5.encode_ids(texts[i], self.max_seq_len) for i in rows])
+            part = special[lo:lo + batch_size]
+            ids, mask = byt5.pad_batch([byt5.encode_ids(t, self.max_seq_len) for _, t in part])
             emb = self._encode(torch.from_numpy(ids).to(self.device), torch.from_numpy(mask).to(self.device))
-            out[torch.tensor(rows, device=self.device)] = emb
+            out[torch.tensor([i for i, _ in part], device=self.device)] = emb
         return out
 
     @torch.no_grad()
@@ -136,13 +166,10 @@ class B200PremiseRetriever:
             return
         assert self.corpus is not None, "load_corpus first"
         premises = self.corpus.all_premises
-        self.corpus_embeddings = torch.zeros(len(premises), self.embedding_size, dtype=self.dtype, device=self.device)
-        # serialise lazily, a chunk at a time, so the regex work overlaps the GPU (see encode_texts)
-        chunk = 1024
-        for lo in range(0, len(premises), chunk):
-            hi = min(len(premises), lo + chunk)
-            self.encode_texts([p.serialize() for p in premises[lo:hi]], batch_size=batch_size,
-                              out=self.corpus_embeddings[lo:hi])
+        self.corpus_embeddings = torch.empty(len(premises), self.embedding_size, dtype=self.dtype, device=self.device)
+        # premises are serialised lazily while encode_texts walks them, so the regex work of group i+1
+        # overlaps the GPU's work on group i
+        self.encode_texts(_Serialized(premises), batch_size=batch_size, out=self.corpus_embeddings)
         self.embeddings_staled = False
 
     # ------------------------------------------------------------------ retrieve (reference :338-375)

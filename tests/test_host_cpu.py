@@ -82,6 +82,63 @@ def test_premise_serialize_marks_own_name():
     assert remove_marks(p.serialize()) == "theorem Nat.Foo.add_zero (n : Nat) : n + 0 = n := rfl"
 
 
+def _serialize_by_regex(full_name: str, code: str) -> str:
+    """The reference rule verbatim in behaviour (common.py:93-106): un-escaped name as a regex."""
+    import re
+    marked = f"<a>{full_name}</a>"
+    text = code.replace(f"_root_.{full_name}", marked)
+    parts = full_name.split(".")
+    for i in range(len(parts)):
+        new = re.sub(f"(?<=\\s)«?{'.'.join(parts[i:])}»?", marked, text)
+        if new != text:
+            return new
+    return text
+
+
+def test_premise_serialize_fast_path_equals_the_regex_rule():
+    """`Premise.serialize` skips the per-premise regex compile for ordinary names; the scan it uses
+    instead must reproduce `re.sub` exactly — overlaps, « » quoting, the any-character dots, the
+    whitespace look-behind, newlines, repeated and adjacent occurrences, suffix fallback."""
+    rng = np.random.default_rng(7)
+    comps = ["Nat", "add", "add_comm", "a", "ab", "foo'", "β", "x1", "Nat", "comm"]
+    glue = [" ", "\n", "\t", ".", "x", "«", "»", "(", ":", "  ", "\u00a0", "_", "a", "Nat", "add", "comm", "ab", "β"]
+    cases = [
+        ("Nat.add_comm", "theorem Nat.add_comm : a + b = b + a"),
+        ("Nat.add_comm", "namespace Nat\ntheorem add_comm (n m : Nat) : n + m = m + n := by\n  exact add_comm n m"),
+        ("Nat.add_comm", "theorem «Nat.add_comm» and NatXadd_comm and Nat\nadd_comm"),
+        ("a.a", " a.a.a aXa a a"),
+        ("ab", " abab ab«ab» «ab» ab"),
+        ("Foo.bar", "lemma _root_.Foo.bar : True"),
+        ("Foo.bar", "no match here"),
+        ("x", "x x  x\nx"),
+    ]
+    for _ in range(4000):
+        k = int(rng.integers(1, 4))
+        name = ".".join(comps[int(i)] for i in rng.integers(0, len(comps), k))
+        pieces = []
+        for _ in range(int(rng.integers(1, 14))):
+            r = rng.random()
+            if r < 0.35:
+                pieces.append(name if rng.random() < 0.5 else name.split(".", 1)[-1])
+            elif r < 0.5:
+                pieces.append(name.replace(".", glue[int(rng.integers(0, len(glue)))]))
+            else:
+                pieces.append(glue[int(rng.integers(0, len(glue)))])
+        cases.append((name, "".join(pieces) or "x"))
+    for name, code in cases:
+        p = Premise("A.lean", name, Pos(1, 0), Pos(2, 0), code)
+        assert p.serialize() == _serialize_by_regex(name, code), (name, code)
+    # names with regex metacharacters / quotes keep the regex path (same rule by construction)
+    for name, code in [("Foo.«bar baz»", "def Foo.«bar baz» := 1"), ("a+b", " aab a+b"), ("f(x", "def f(x")]:
+        try:
+            want = _serialize_by_regex(name, code)
+        except Exception as e:  # the reference raises on an invalid pattern; so do we
+            with pytest.raises(type(e)):
+                Premise("A.lean", name, Pos(1, 0), Pos(2, 0), code).serialize()
+            continue
+        assert Premise("A.lean", name, Pos(1, 0), Pos(2, 0), code).serialize() == want
+
+
 def test_corpus_accessibility_and_mask():
     corpus = _toy_corpus()
     assert len(corpus) == 8 and corpus.num_files == 4 and "C.lean" in corpus
