@@ -308,6 +308,8 @@ def run_engine(args) -> dict:
                          "frac": max(t_mma, t_hbm) / (ms_r / 1e3), "hbm_frac": t_hbm / (ms_r / 1e3),
                          "note": "whole retrieve (sim kernel + select/rescore [+ gather/merge]) vs max(t_MMA, t_HBM) of the sim kernel"},
         }
+        if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+            retrieve["cpu_baseline"] = cpu_baseline_retrieve(E, Q, k)
 
     result = {
         "metric": "premises encoded/sec (reindex_corpus, ByT5-small, seq_len<=512)",
@@ -354,6 +356,23 @@ def cpu_baseline_encode(cfg, sd, data, offsets, n_premises: int, precision: str 
     return {"value": n_premises / dt, "unit": "premises/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
             "kind": "port", "sample": f"first {n_premises} premises of the cfg2 corpus, batch 64 pad-to-longest, fp32 matmul precision '{precision}', {dt:.1f} s",
             "note": "oracle/reference_path.py = reference algorithm on HF T5EncoderModel (the reference modules need lean_dojo/lightning/deepspeed, absent here)"}
+
+
+def cpu_baseline_retrieve(E_dev: torch.Tensor, Q_dev: torch.Tensor, k: int, n_queries: int = 64) -> dict:
+    """Reference retrieve arithmetic on the host cores (common.py:307-324: fp32 matmul, full argsort,
+    .tolist(), Python walk) for a bounded sample of the same queries against the same index."""
+    from oracle import reference_path as ref
+
+    torch.set_float32_matmul_precision("medium")
+    E = E_dev.float().cpu()
+    Q = Q_dev[:n_queries].float().cpu()
+    ref.nearest_unfiltered_verbatim(E, Q[:1], k)  # warm-up
+    t0 = time.perf_counter()
+    ref.nearest_unfiltered_verbatim(E, Q, k)
+    dt = time.perf_counter() - t0
+    torch.set_float32_matmul_precision("highest")
+    return {"value": n_queries / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{n_queries} of the 1024 states against the full {E.shape[0]}-row fp32 index, k={k}, {dt:.1f} s"}
 
 
 def run_reference(args) -> dict:

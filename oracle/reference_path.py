@@ -114,6 +114,24 @@ def get_nearest_premises(corpus, premise_embeddings: torch.Tensor, batch_context
     return results, scores
 
 
+def nearest_unfiltered_verbatim(premise_embeddings: torch.Tensor, batch_context_emb: torch.Tensor, k: int):
+    """common.py:307-324 with the reference's own cost profile (used as the CPU stopwatch of the
+    retrieve leg, not for parity): fp32 `@`, full `argsort(descending=True)` of all N scores per
+    query, `.tolist()` of the whole order, Python walk taking the first k, `.item()` per score.
+    Every premise is accessible here (BASELINE config 3 has no accessibility filter)."""
+    similarities = batch_context_emb @ premise_embeddings.t()
+    idxs_batch = similarities.argsort(dim=1, descending=True).tolist()
+    results = [[] for _ in idxs_batch]
+    scores = [[] for _ in idxs_batch]
+    for j, idxs in enumerate(idxs_batch):
+        for i in idxs:
+            results[j].append(i)
+            scores[j].append(similarities[j, i].item())
+            if len(results[j]) >= k:
+                break
+    return results, scores
+
+
 def topk_plain(q: torch.Tensor, e: torch.Tensor, k: int, mask: Optional[np.ndarray] = None):
     """Top-k without a corpus object: (indices [Q,k] int64, fp64 scores [Q,k]); `mask` [Q,N] bool."""
     sims = similarities_fp64(q, e)
