@@ -154,3 +154,34 @@ def test_many_short_sequences_and_chunking(rpx_lib, cuda_device, tiny):
     want = oracle_embeddings(cfg, sd, data[: offsets[40]], offsets[:41], 64, batch_size=40)
     max_abs, min_cos = compare_embeddings(a[:40], want)
     assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
+
+
+def test_byt5_small_full_size_batch_invariance(rpx_lib, cuda_device):
+    """BASELINE config 2 geometry at a size where every pipelined path is busy: 1500 premises = one
+    full 262,144-token engine call (74 CTA pairs x ~83 tiles each: operand ring, TMEM double buffer
+    and the residual TMA ring all run across many tile boundaries) plus a ragged tail call.  An
+    embedding must not depend on what else is in the batch — bit for bit: every output row sums its
+    products in an order fixed by the kernel shapes, not by the tile, the pair or the call it lands
+    in — and the sampled rows must still match the fp32 oracle."""
+    cfg = dict(synth.BYT5_SMALL)
+    sd = synth.random_t5_state_dict(cfg, seed=synth.SEED)
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    n = 1500
+    data, offsets = synth.synth_premises(n, seed=synth.SEED + 5)
+    tokens = np.minimum(np.diff(offsets) + 1, 512)
+    assert tokens.sum() > eng.max_tokens_per_call, "the batch must span more than one engine call"
+    big = eng.encode_bytes(data, offsets, 512, out_dtype=torch.float32)
+    assert torch.isfinite(big).all()
+    norms = big.norm(dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=2e-3)
+    # rows around the call boundary, the first and last rows, and a stride through the middle
+    cut = int(np.searchsorted(np.cumsum(tokens), eng.max_tokens_per_call, side="right"))
+    picks = sorted({0, 1, 2, cut - 2, cut - 1, cut, cut + 1, n - 2, n - 1, *range(97, n, 211)})
+    blobs = [bytes(data[offsets[i]:offsets[i + 1]]) for i in picks]
+    sub_off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])]).astype(np.int64)
+    sub_data = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    alone = eng.encode_bytes(sub_data, sub_off, 512, out_dtype=torch.float32)
+    assert torch.equal(alone, big[torch.tensor(picks, device=big.device)])
+    want = oracle_embeddings(cfg, sd, sub_data[: sub_off[6]], sub_off[:7], 512, batch_size=6)
+    max_abs, min_cos = compare_embeddings(alone[:6], want)
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
