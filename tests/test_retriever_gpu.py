@@ -182,3 +182,25 @@ def test_validation_and_predict_steps(setup):
         assert len(recs[0]["scores"]) == 10
     finally:
         r.num_retrieved = old_k
+
+
+def test_reindex_does_not_depend_on_the_token_budget(setup):
+    """`reindex_corpus` streams premises to the engine in groups cut by the engine's token budget.
+    With a budget small enough to force a dozen groups — one of them split around the premise that
+    takes the host-tokenised ids path — the index must equal the one built with a single group."""
+    r = setup["retr"]
+    base = r.corpus_embeddings.clone()
+    saved = r.encoder.max_tokens_per_call
+    try:
+        for budget in (MAX_LEN, 1500, 4000):
+            r.encoder.max_tokens_per_call = budget
+            r.embeddings_staled = True
+            r.reindex_corpus(batch_size=3)
+            assert not r.embeddings_staled
+            assert torch.equal(r.corpus_embeddings, base), budget
+    finally:
+        r.encoder.max_tokens_per_call = saved
+    # a lazily produced sequence and a list are the same thing to encode_texts
+    texts = [p.serialize() for p in r.corpus.all_premises]
+    assert torch.equal(r.encode_texts(texts), base)
+    assert torch.equal(r.encode_texts(texts[40:55]), base[40:55])
