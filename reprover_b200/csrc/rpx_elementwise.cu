@@ -109,7 +109,33 @@ __global__ void pool_normalize_kernel(const float* __restrict__ h32, const float
   const bool active = i < d_model / 4;
   const float inv_d = 1.0f / (float)d_model;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = t0; t < t1; ++t) {
+  // four tokens per trip: all loads of the trip go out before the first dependent FMA (one CTA per
+  // sequence keeps only ~1.5 KB in flight per token row otherwise); accumulation order is still t0..t1
+  constexpr int kU = 4;
+  int t = t0;
+  for (; t + kU <= t1; t += kU) {
+    float4 v[kU];
+    float sum[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      v[u] = active ? reinterpret_cast<const float4*>(h32 + (int64_t)(t + u) * d_model)[i]
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum[u] = 0.f;
+    }
+    for (int p = 0; p < n_parts; ++p) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) sum[u] += ss[(int64_t)p * ss_stride + t + u];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const float rs = rsqrtf(sum[u] * inv_d + eps);
+      acc.x += v[u].x * rs;
+      acc.y += v[u].y * rs;
+      acc.z += v[u].z * rs;
+      acc.w += v[u].w * rs;
+    }
+  }
+  for (; t < t1; ++t) {
     float sum = 0.f;
     for (int p = 0; p < n_parts; ++p) sum += ss[(int64_t)p * ss_stride + t];
     const float rs = rsqrtf(sum * inv_d + eps);
