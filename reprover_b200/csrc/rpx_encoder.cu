@@ -10,8 +10,8 @@
 //     h32  [T, D] fp32   residual stream (master copy)
 //     h16  [T, D] bf16   same values, GEMM A operand
 //     qkv  [T, 3*H*64] bf16,  attn [T, H*64] bf16,  ffn [T, d_ff] bf16
-//     ssA / ssB [12][T] fp32  per-row partial sums of h32^2 (two per 256-column output
-//                             block of the GEMM that produced h32) -> RMSNorm row scale
+//     ssA / ssB [n_parts][T] fp32  per-row partial sums of h32^2, one per n-tile of the GEMM that
+//                             produced h32 (6 for d_model = 1472) -> RMSNorm row scale
 // RMSNorm never runs as its own kernel: its weight vector is folded into the next
 // GEMM's B operand when the weights are packed, and the row scale rsqrt(mean(h^2)+eps)
 // is applied to the fp32 accumulator in that GEMM's epilogue (rpx_gemm.cuh RowScale).
