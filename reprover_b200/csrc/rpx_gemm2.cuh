@@ -47,6 +47,16 @@ RPX_DEVICE void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar,
         "r"(c0), "r"(c1)
       : "memory");
 }
+RPX_DEVICE void tma_load_2d_2sm_hint(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                     uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask),
+        "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 RPX_DEVICE void tmem_alloc_2sm(uint32_t* dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols)
                : "memory");
@@ -125,7 +135,27 @@ __device__ __forceinline__ void n_tile_range(int n_blk, int N, int tiles_n, int&
   n_this = 32 * (base + (n_blk >= first_wide ? 1 : 0));
 }
 
-template <int STAGES, class Epi>
+// Tile -> (row block of 256, n-tile origin / width).  Default: n fastest, near-equal n-tiles.
+// M_FASTEST (the similarity kernel): the pair grid is a multiple of tiles_m, so a pair keeps ONE row
+// block (its two query blocks) for all its tiles and walks the corpus in fixed 256-wide tiles; the
+// last tile may be ragged (width rounded up to 32: TMA zero-fills, the epilogue masks by N).
+template <bool M_FASTEST>
+__device__ __forceinline__ void decode_tile(int tile, int N, int tiles_m, int tiles_n, int& m_blk, int& n_blk,
+                                            int& n0, int& n_this) {
+  if (M_FASTEST) {
+    m_blk = tile % tiles_m;
+    n_blk = tile / tiles_m;
+    n0 = n_blk * 256;
+    const int rest = (N - n0 + 31) & ~31;
+    n_this = rest < 256 ? rest : 256;
+  } else {
+    n_blk = tile % tiles_n;
+    m_blk = tile / tiles_n;
+    n_tile_range(n_blk, N, tiles_n, n0, n_this);
+  }
+}
+
+template <int STAGES, class Epi, bool M_FASTEST = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                 int tiles_m, int tiles_n, const __grid_constant__ typename Epi::Params ep) {
@@ -182,17 +212,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int n_blk = tile % tiles_n;
-        const int m_blk = tile / tiles_n;
-        int n0, n_this;
-        n_tile_range(n_blk, N, tiles_n, n0, n_this);
+        int m_blk, n_blk, n0, n_this;
+        decode_tile<M_FASTEST>(tile, N, tiles_m, tiles_n, m_blk, n_blk, n0, n_this);
         const int a_row = m_blk * kPairM + (int)rank * kBlockM;
         const int b_row = n0 + (int)rank * (n_this / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
-          tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, a_row);
-          tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK, b_row);
+          if (M_FASTEST) {
+            // the row block is re-read by every tile of this pair, the other operand is streamed once
+            // (same L2 policy as the 1-CTA similarity kernel: -20 % there)
+            tma_load_2d_2sm_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, a_row, kEvictLast);
+            tma_load_2d_2sm_hint(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK, b_row, kEvictFirst);
+          } else {
+            tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, a_row);
+            tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK, b_row);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -208,8 +243,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        int n0, n_this;
-        n_tile_range(tile % tiles_n, N, tiles_n, n0, n_this);
+        int m_blk, n_blk, n0, n_this;
+        decode_tile<M_FASTEST>(tile, N, tiles_m, tiles_n, m_blk, n_blk, n0, n_this);
         const uint32_t idesc = make_idesc_bf16(kPairM, (uint32_t)n_this);
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
@@ -243,12 +278,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     for (int tile = pair; tile < num_tiles; tile += n_pairs) {
       TileCtx t;
-      t.n_blk = tile % tiles_n;
-      t.m_blk = tile / tiles_n;
-      t.m0 = t.m_blk * kPairM + (int)rank * kBlockM;
       int n_this;
-      n_tile_range(t.n_blk, N, tiles_n, t.n0, n_this);
-      t.n_cols = n_this < N - t.n0 ? n_this : N - t.n0;
+      decode_tile<M_FASTEST>(tile, N, tiles_m, tiles_n, t.m_blk, t.n_blk, t.n0, n_this);
+      t.m0 = t.m_blk * kPairM + (int)rank * kBlockM;
+      t.n_cols = n_this < N - t.n0 ? n_this : ((N - t.n0 + 31) & ~31);
       t.row = row;
       t.part = part;
       t.split = Epi::kWarps / 4;
@@ -258,8 +291,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       {
         const int nt = tile + n_pairs;
         if (nt < num_tiles) {
-          t.next_m0 = (nt / tiles_n) * kPairM + (int)rank * kBlockM;
-          n_tile_range(nt % tiles_n, N, tiles_n, t.next_n0, t.next_cols);
+          int nm, nn;
+          decode_tile<M_FASTEST>(nt, N, tiles_m, tiles_n, nm, nn, t.next_n0, t.next_cols);
+          t.next_m0 = nm * kPairM + (int)rank * kBlockM;
           if (t.next_cols > N - t.next_n0) t.next_cols = N - t.next_n0;
         } else {
           t.next_m0 = -1;

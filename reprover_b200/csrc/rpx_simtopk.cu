@@ -33,6 +33,9 @@ constexpr int kSimBlockN = 256;
 #define RPX_SIM_SEL_SLACK 16
 #endif
 constexpr int kSampleTiles = RPX_SIM_SAMPLE_TILES;  // 32 x 256 = 8192 sampled premises
+#ifndef RPX_SIM_2CTA
+#define RPX_SIM_2CTA 1  // 0: stage 1 always on the 1-CTA kernel
+#endif
 constexpr int kSelSlack = RPX_SIM_SEL_SLACK;        // stage 2 re-scores between n_res and n_res + kSelSlack rows
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -43,27 +46,33 @@ __device__ __forceinline__ uint32_t unkey(uint32_t k) { return (k & 0x80000000u)
 // EPL = candidate entries per lane: a list holds CAP = 32*EPL entries and is compacted back to
 // about KEEP (<= CAP/2) when it fills.  KEEP is the size of the candidate superset a CTA
 // guarantees for its slice of the corpus.
-template <int EPL, int KEEP_>
+// Stage-1 epilogue parameters (shared by every EpiSimTopk instantiation).
+struct SimTopkParams {
+  uint2* cand;           // [grid][128][CAP]  (score bits, local index)
+  int32_t* cnt;          // [grid][128]
+  uint32_t* gthr;        // [tiles_m*128] shared per-query threshold (monotone key, atomicMax)
+  uint32_t* gmin;        // [tiles_m*128] min over CTAs of their first published rank_r-th best key
+  uint32_t* gcnt;        // [tiles_m*128] number of CTAs that have published into gmin
+  int n_seg;             // CTAs per query block
+  int rank_r;            // ceil(KEEP / n_seg)
+  int final_max;         // longest list stage 2 accepts (CAP: no final compaction; else KEEP+SLACK)
+  const uint32_t* mask;  // optional access bitmask [nq][mask_stride]
+  int64_t mask_stride;
+  int nq;
+  int n;
+  int tiles_m;
+};
+
+// PAIRED: the epilogue runs inside the 2-CTA (cta_group::2) kernel.  CTA `rank` of pair p serves query
+// block 2*(p % (tiles_m/2)) + rank and corpus segment p / (tiles_m/2); lists, counters and stage 2 keep
+// the 1-CTA numbering  cta = query_block + segment * tiles_m.
+template <int EPL, int KEEP_, bool PAIRED = false>
 struct EpiSimTopk {
   static constexpr int CAP = 32 * EPL;
   static constexpr int KEEP = KEEP_;
   static constexpr int SLACK = 16;
   static_assert(KEEP + SLACK + 32 <= CAP, "list too small");
-  struct Params {
-    uint2* cand;           // [grid][128][CAP]  (score bits, local index)
-    int32_t* cnt;          // [grid][128]
-    uint32_t* gthr;        // [tiles_m*128] shared per-query threshold (monotone key, atomicMax)
-    uint32_t* gmin;        // [tiles_m*128] min over CTAs of their first published rank_r-th best key
-    uint32_t* gcnt;        // [tiles_m*128] number of CTAs that have published into gmin
-    int n_seg;             // CTAs per query block
-    int rank_r;            // ceil(KEEP / n_seg)
-    int final_max;         // longest list stage 2 accepts (CAP: no final compaction; else KEEP+SLACK)
-    const uint32_t* mask;  // optional access bitmask [nq][mask_stride]
-    int64_t mask_stride;
-    int nq;
-    int n;
-    int tiles_m;
-  };
+  using Params = SimTopkParams;
   static constexpr size_t kSmemBytes = 0;
   static constexpr int kWarps = 4;  // one warp per TMEM lane group: a query's list has one writer
 
@@ -79,17 +88,22 @@ struct EpiSimTopk {
 
   __device__ EpiSimTopk(const Params& p_, uint8_t*, int row, int) : p(p_) {
     lane = row & 31;
-    q = (blockIdx.x % p.tiles_m) * kBlockM + row;
+    int cta = blockIdx.x;
+    if (PAIRED) {
+      const int pair = blockIdx.x >> 1, half = p.tiles_m >> 1;
+      cta = 2 * (pair % half) + (int)cluster_ctarank() + (pair / half) * p.tiles_m;
+    }
+    q = (cta % p.tiles_m) * kBlockM + row;
     active = q < p.nq;
 #ifdef RPX_SIM_NOAPPEND  // tuning experiment: mainloop + TMEM read + compare floor (results are wrong)
     thr = INFINITY;
 #else
     thr = -INFINITY;
 #endif
-    warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + (row & ~31)) * CAP;
+    warp_buf = p.cand + ((size_t)cta * kBlockM + (row & ~31)) * CAP;
     buf = warp_buf + (size_t)lane * CAP;
     wptr = buf;
-    slot = blockIdx.x * kBlockM + row;
+    slot = cta * kBlockM + row;
   }
   __device__ __forceinline__ int count() const { return (int)(wptr - buf); }
 
@@ -688,6 +702,7 @@ struct SimPlan {
   int epl, cap, keep, list_max, n_res;
   size_t sel_smem;
   int tiles_m, grid;
+  bool paired;  // stage 1 on the 2-CTA kernel: tiles_m is even, grid = 2 * pairs
   size_t cand_bytes, cnt_bytes, gthr_bytes, sample_bytes, total;
   int sample_tiles;  // corpus tiles scored by the sampling pass (0 = no sampling pass)
 };
@@ -710,7 +725,12 @@ int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
   pl->cap = 32 * pl->epl;
   int chunk_q = nq < num_sms * kBlockM ? nq : num_sms * kBlockM;  // queries per launch
   pl->tiles_m = ceil_div(chunk_q, kBlockM);
-  int n_seg = num_sms / pl->tiles_m;
+  // two or more query blocks: stage 1 runs on CTA pairs (256 queries x 256 premises per tcgen05
+  // instruction); an odd block count is padded with an inactive block
+  pl->paired = RPX_SIM_2CTA && pl->tiles_m >= 2;
+  if (pl->paired) pl->tiles_m += pl->tiles_m & 1;
+  int n_seg = pl->paired ? (num_sms / 2) / (pl->tiles_m / 2) : num_sms / pl->tiles_m;
+  if (n_seg < 1) n_seg = 1;
   // stage 2 keeps one query's lists in shared memory: full-length lists if they fit, else lists
   // compacted to KEEP+16 at the end of stage 1, else fewer stage-1 CTAs per query block
   // (short lists => small stage-2 footprint => several stage-2 CTAs per SM to hide the gather latency)
@@ -757,6 +777,34 @@ int launch_sim_epi(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64
   const int grid = tiles < pl.grid ? (int)tiles : pl.grid;  // stays a multiple of tiles_m
   kern<<<grid, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, stride,
                                                 ep);
+  RPX_CUDA_OK(cudaGetLastError());
+  return RPX_OK;
+}
+
+// Stage 1 on the 2-CTA kernel (plan.paired): pairs = (tiles_m / 2) x segments.
+template <class Epi>
+int launch_sim_epi_paired(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64_t n, int d,
+                          const typename Epi::Params& ep, const SimPlan& pl, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<kGemm2Stages>;
+  DeviceInfo dev;
+  RPX_TRY(get_device_info(&dev));
+  CUtensorMap tmA, tmB;
+  RPX_TRY(make_tmap_bf16_2d(&tmA, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, kBlockM));
+  RPX_TRY(make_tmap_bf16_2d(&tmB, E, (uint64_t)n, (uint64_t)d, (uint64_t)d, Cfg::kBlockN / 2));
+  const int tiles_m2 = pl.tiles_m / 2;
+  const int tiles_n = (int)ceil_div64(n, kSimBlockN);
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "sim: needs %zu B smem, device allows %zu", smem,
+              dev.smem_optin);
+  auto kern = gemm_tc2_kernel<kGemm2Stages, Epi, true>;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != dev.device) {
+    RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev.device;
+  }
+  const int64_t tiles = (int64_t)tiles_m2 * tiles_n;
+  const int pairs = tiles < pl.grid / 2 ? (int)tiles : pl.grid / 2;  // stays a multiple of tiles_m2
+  kern<<<2 * pairs, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, tiles_m2, tiles_n, ep);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }
@@ -829,11 +877,16 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
       RPX_CUDA_OK(cudaGetLastError());
     }
     if (n > 0) {
-      if (pl.keep == 128) {
-        EpiSimTopk<16, 128>::Params ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+      SimTopkParams ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+      if (pl.paired) {
+        if (pl.keep == 128) {
+          RPX_TRY((launch_sim_epi_paired<EpiSimTopk<16, 128, true>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+        } else {
+          RPX_TRY((launch_sim_epi_paired<EpiSimTopk<16, 256, true>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
+        }
+      } else if (pl.keep == 128) {
         RPX_TRY((launch_sim_epi<EpiSimTopk<16, 128>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       } else {
-        EpiSimTopk<16, 256>::Params ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
         RPX_TRY((launch_sim_epi<EpiSimTopk<16, 256>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       }
     }
