@@ -260,14 +260,17 @@ def run_engine(args) -> dict:
         E = synth.random_unit_rows(n_idx, D_MODEL, 1000 + rank, dev)
         Q = synth.random_unit_rows(nq, D_MODEL, 999, dev)   # same queries on every rank
         Q_host = Q.cpu().pin_memory()
-        reps = max(3, K)
+        # one retrieve is ~0.6 ms: a handful of repetitions would be timed while the SM clock is still
+        # ramping after the host-side legs; 50 repetitions (~30 ms) after 10 warm-ups are past that
+        reps = max(50, K)
+        warm_r = max(10, W)
 
         def retrieve_dev():
             if world == 1:
                 return sim_topk(Q, E, k)
             return sharded_topk(Q, E, k, row_offset=rank * n_idx)
 
-        for _ in range(3):
+        for _ in range(warm_r):
             retrieve_dev()
         barrier(world)
         e0.record()
@@ -287,7 +290,8 @@ def run_engine(args) -> dict:
             res_idx.copy_(r[1], non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the host result here
 
-        retrieve_host()   # warm-up (allocator, pinned staging)
+        for _ in range(3):
+            retrieve_host()   # warm-up (allocator, pinned staging)
         barrier(world)
         e0.record()
         for _ in range(reps):
@@ -301,7 +305,8 @@ def run_engine(args) -> dict:
         t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
         retrieve = {
             "metric": "retrieve queries/s", "config": {"queries": nq, "index_rows_per_gpu": n_idx, "index_rows_total": n_idx * world,
-                                                      "k": k, "dtype": "bf16", "merge": "nccl all_gather + device merge" if world > 1 else "none"},
+                                                      "k": k, "dtype": "bf16", "merge": "nccl all_gather + device merge" if world > 1 else "none",
+                                                      "warmup": warm_r, "repetitions": reps},
             "value": nq / (ms_r / 1e3), "ms": ms_r,
             "e2e": {"value": nq / (ms_re / 1e3), "ms": ms_re, "h2d_bytes": nq * D_MODEL * 2, "d2h_bytes": nq * k * 12},
             "roofline": {"bound": "tensor", "achieved": flops / (ms_r / 1e3) / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",

@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 # full captures: layer 0 of the first 262144-token chunk, and one retrieve (1024 x 200k, k = 100)
 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc2_kernel|t5_attention' -s 0 -c 5 -f \
     -o gpurun_out/prof_${TAG}_encode python tools/profile_step.py --mode encode --layers 2 --premises 1024 --warm 0 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc_kernel|select_rescore|sample_threshold' -s 0 -c 4 -f \
+ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc2?_kernel|select_rescore|sample_threshold' -s 0 -c 4 -f \
     -o gpurun_out/prof_${TAG}_retrieve python tools/profile_step.py --mode retrieve --warm 0 > /dev/null 2>&1
 ls -la gpurun_out/*${TAG}*
 head -c 1500 gpurun_out/bench_${TAG}.json
