@@ -34,19 +34,9 @@ namespace rpx {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kUmmaK = 16;
-#ifndef RPX_PREFETCH_KB
-#define RPX_PREFETCH_KB 0
-#endif
-#ifndef RPX_TMA_HINTS
-#define RPX_TMA_HINTS 0
-#endif
-#ifndef RPX_EPI_HINTS
-#define RPX_EPI_HINTS 0
-#endif
 #ifndef RPX_EPI_WARPS
 #define RPX_EPI_WARPS 4
 #endif
-constexpr int kPrefetchKb = RPX_PREFETCH_KB;  // L2 prefetch distance of the streamed operand, in k-blocks (0 = off)
 constexpr int kEpiWarp0 = 2;  // first epilogue warp
 // threads of a launch: TMA warp + MMA warp + Epi::kWarps epilogue warps (4 or 8)
 template <class Epi>
@@ -147,33 +137,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
-          // Optional (off by default, RPX_PREFETCH_KB): pull the streamed operand into L2 a few
-          // k-blocks ahead of its shared-memory load.  Measured on B200 (A/B on one box, round 1):
-          // distance 8 made every GEMM 6-12 % SLOWER, so it stays disabled.
-          if (kPrefetchKb == 0) {
-          } else if (kb + kPrefetchKb < num_kb) {
-            if (M_FASTEST) tma_prefetch_2d(&tmB, (kb + kPrefetchKb) * kBlockK, n_blk * BLOCK_N);
-            else tma_prefetch_2d(&tmA, (kb + kPrefetchKb) * kBlockK, m_blk * kBlockM);
-          } else {
-            const int nt = tile + gridDim.x;
-            if (nt < num_tiles) {
-              const int kb2 = kb + kPrefetchKb - num_kb;
-              if (kb2 < num_kb) {
-                if (M_FASTEST) tma_prefetch_2d(&tmB, kb2 * kBlockK, (nt / tiles_m) * BLOCK_N);
-                else tma_prefetch_2d(&tmA, kb2 * kBlockK, (nt / tiles_n) * kBlockM);
-              }
-            }
-          }
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          if (M_FASTEST || RPX_TMA_HINTS) {
+          if (M_FASTEST) {
             // L2 eviction hints: streamed operand evict-first, re-used operand evict-last.  Measured
             // on B200 (A/B, one box): -20 % time for the similarity kernel (corpus streamed once, query
-            // block re-read by every tile), +3 % for the encoder GEMMs -> on for M_FASTEST only.
-            tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM,
-                             M_FASTEST ? kEvictLast : kEvictFirst);
+            // block re-read by every tile), +3 % for the encoder GEMMs -> M_FASTEST only.  (An L2
+            // prefetch of the streamed operand a few k-blocks ahead of its TMA load was also measured:
+            // 6-12 % slower at every distance tried, removed.)
+            tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM, kEvictLast);
             tma_load_2d_hint(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
-                             n_blk * n_blk_stride * BLOCK_N, M_FASTEST ? kEvictFirst : kEvictLast);
+                             n_blk * n_blk_stride * BLOCK_N, kEvictFirst);
           } else {
             tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
@@ -378,12 +352,9 @@ struct EpiStoreBF16 {
 // one instruction covers 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32).
 // Residual loads run one chunk ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting the chunks — was measured
 // neutral to slightly negative on B200 and is off by default.)
-// L2 prefetch of the next tile's residual rows (one tile ahead).  It paid while this epilogue also
-// served the K = 384 projection; for the tensor-bound K = 3584 one the lines are evicted again before
-// use (ncu: 6.0 GB read against 3.4 GB algorithmic), so it is off: -1.6 % on that GEMM.
-#ifndef RPX_RES_L2_PREFETCH
-#define RPX_RES_L2_PREFETCH 0
-#endif
+// (Measured and dropped: an L2 prefetch of the next tile's residual rows one tile ahead — the lines
+// were evicted again before use, 6.0 GB read per launch against 3.4 GB algorithmic — and L2
+// eviction-priority hints on the residual loads / stores, 0 %.)
 struct EpiResidual {
   struct Params {
     float* h32;
@@ -397,40 +368,19 @@ struct EpiResidual {
   Params p;
   float4* stg;  // this warp's staging tile: row r = 8 float4, stored at slot (j ^ (r & 7))
   int lane, grp;
-  uint64_t pol;
   __device__ EpiResidual(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
-    pol = l2_policy_evict_first();
     lane = row & 31;
     grp = row >> 5;
     stg = reinterpret_cast<float4*>(smem_extra) + (part * 4 + grp) * 32 * 8;
   }
-  // Called right before this tile's accumulator is awaited: pull the residual rows of the NEXT
-  // tile into L2 now, so that by the time they are read-modify-written (one epilogue from now)
-  // the loads are L2 hits.  One 128-byte line per prefetch; row = lane.
-  __device__ void before_wait(const TileCtx& t) {
-#if !RPX_RES_L2_PREFETCH
-    return;
-#endif
-    if (t.next_m0 < 0) return;
-    const int m = t.next_m0 + grp * 32 + lane;
-    if (m < t.M) {
-      const float* rowp = p.h32 + (size_t)m * p.ld + t.next_n0;
-      const int n_cols = t.next_cols;
-      for (int c = 32 * t.part; c < n_cols; c += 32 * t.split)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + c));
-    }
-  }
+  __device__ void before_wait(const TileCtx&) {}
   __device__ __forceinline__ void load_chunk(const TileCtx& t, int c, int row_base, int sub, int col4,
                                              float4 (&h)[8]) const {
     const size_t col = (size_t)t.n0 + c + col4;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = row_base + sub + 4 * i;
-#if RPX_EPI_HINTS
-      if (m < t.M) h[i] = ld_f4_hint(p.h32 + (size_t)m * p.ld + col, pol);
-#else
       if (m < t.M) h[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
-#endif
       else h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -470,11 +420,7 @@ struct EpiResidual {
         h[i].w += a.w;
         ss[i] += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
         if (m < t.M) {
-#if RPX_EPI_HINTS
-          st_f4_hint(p.h32 + (size_t)m * p.ld + col, h[i], pol);
-#else
           *reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + col) = h[i];
-#endif
           *reinterpret_cast<uint2*>(p.h16 + (size_t)m * p.ld + col) =
               make_uint2(pack_bf16x2(h[i].x, h[i].y), pack_bf16x2(h[i].z, h[i].w));
         }

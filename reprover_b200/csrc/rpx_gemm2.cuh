@@ -119,15 +119,7 @@ struct Gemm2Cfg {
 // out of step and A came from DRAM ~3x instead of once (ncu: 7.1 GB read for the FFN
 // down-projection against 3.4 GB algorithmic).  224/224/256/256/256/256 gives every pair the same
 // work per three tiles.
-#ifndef RPX_GEMM2_EVEN_SPLIT
-#define RPX_GEMM2_EVEN_SPLIT 1  // 0: full tiles + short tail (kept for A/B runs)
-#endif
 __device__ __forceinline__ void n_tile_range(int n_blk, int N, int tiles_n, int& n0, int& n_this) {
-#if !RPX_GEMM2_EVEN_SPLIT
-  n0 = n_blk * 256;
-  n_this = N - n0 > 256 ? 256 : ((N - n0 + 31) & ~31);
-  return;
-#endif
   const int units = (N + 31) >> 5;
   const int base = units / tiles_n;
   const int first_wide = tiles_n - (units - base * tiles_n);

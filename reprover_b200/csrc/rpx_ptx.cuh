@@ -140,13 +140,6 @@ template <int N>
 RPX_DEVICE void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-// L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking).
-RPX_DEVICE void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -254,31 +247,6 @@ RPX_DEVICE uint64_t make_smem_desc_kmajor_sw128(uint32_t smem_addr) {
 //   n_dim [17,23) = N >> 3          m_dim [24,29) = M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
-}
-
-// ----------------------------------------------------------------------------- L2 cache-hinted global access
-// Streaming traffic (touched once) is tagged evict-first so it does not push re-used operand tiles
-// out of L2.
-RPX_DEVICE uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-RPX_DEVICE float4 ld_f4_hint(const float* ptr, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(policy));
-  return v;
-}
-RPX_DEVICE void st_f4_hint(float* ptr, float4 v, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w), "l"(policy)
-               : "memory");
-}
-RPX_DEVICE void st_u2_hint(void* ptr, uint2 v, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(ptr), "r"(v.x), "r"(v.y), "l"(policy)
-               : "memory");
 }
 
 // ----------------------------------------------------------------------------- misc

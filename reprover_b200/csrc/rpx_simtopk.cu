@@ -95,11 +95,7 @@ struct EpiSimTopk {
     }
     q = (cta % p.tiles_m) * kBlockM + row;
     active = q < p.nq;
-#ifdef RPX_SIM_NOAPPEND  // tuning experiment: mainloop + TMEM read + compare floor (results are wrong)
-    thr = INFINITY;
-#else
     thr = -INFINITY;
-#endif
     warp_buf = p.cand + ((size_t)cta * kBlockM + (row & ~31)) * CAP;
     buf = warp_buf + (size_t)lane * CAP;
     wptr = buf;
