@@ -241,7 +241,13 @@ class Corpus:
         self.all_premises: List[Premise] = []
         self._files: Dict[str, File] = {}
         self._range: Dict[str, Tuple[int, int]] = {}
-        self._deps: Dict[str, frozenset] = {}  # transitive imports
+        # transitive imports as bit sets over the files' insertion order (bit i = self._order[i]):
+        # a Python int per file keeps a mathlib-sized import closure (5 k files, each importing most
+        # of its predecessors) at ~3 MB and a union at one big-int OR, where sets of path strings
+        # cost ~200 MB and quadratic time
+        self._order: List[str] = []
+        self._index: Dict[str, int] = {}
+        self._dep_bits: Dict[str, int] = {}
         self.imported_premises_cache: Dict[str, List[Premise]] = {}
         if jsonl_path is not None:
             with open(jsonl_path) as fh:
@@ -254,6 +260,23 @@ class Corpus:
         state.pop("_import_words_cache", None)  # derived data: keep index pickles lean
         return state
 
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if "_dep_bits" not in state:  # pickles written before the bit-set representation
+            self._order = list(self._files)
+            self._index = {p: i for i, p in enumerate(self._order)}
+            old = state.get("_deps", {})
+            self._dep_bits = {p: sum(1 << self._index[d] for d in old.get(p, ())) for p in self._order}
+            self.__dict__.pop("_deps", None)
+
+    def _dep_paths(self, path: str) -> Generator[str, None, None]:
+        """Files `path` imports (transitively), in corpus order."""
+        bits = self._dep_bits[path]
+        while bits:
+            low = bits & -bits
+            yield self._order[low.bit_length() - 1]
+            bits ^= low
+
     @classmethod
     def from_files(cls, files: Iterable[Tuple[File, Iterable[str]]]) -> "Corpus":
         c = cls()
@@ -263,16 +286,17 @@ class Corpus:
 
     def _add_file(self, f: File, imports: List[str]) -> None:
         assert f.path not in self._files, f"duplicate file {f.path}"
-        closure = set()
+        closure = 0
         for imp in imports:
             assert imp in self._files, f"{f.path} imports {imp} before it is defined"
-            closure.add(imp)
-            closure |= self._deps[imp]
+            closure |= (1 << self._index[imp]) | self._dep_bits[imp]
         lo = len(self.all_premises)
         self.all_premises.extend(f.premises)
         self._files[f.path] = f
         self._range[f.path] = (lo, len(self.all_premises))
-        self._deps[f.path] = frozenset(closure)
+        self._index[f.path] = len(self._order)
+        self._order.append(f.path)
+        self._dep_bits[f.path] = closure
 
     # ---- reference-compatible accessors ------------------------------------------------
     def _get_file(self, path: str) -> File:
@@ -296,7 +320,7 @@ class Corpus:
         return len(self._files)
 
     def get_dependencies(self, path: str) -> List[str]:
-        return [p for p in self._files if p in self._deps[path]]
+        return list(self._dep_paths(path))
 
     def get_premises(self, path: str) -> List[Premise]:
         return self._files[path].premises
@@ -358,7 +382,7 @@ class Corpus:
         """
         pos = Pos.from_any(pos)
         mask = np.zeros(len(self.all_premises), dtype=bool)
-        for dep in self._deps[path]:
+        for dep in self._dep_paths(path):
             a, b = self._range[dep]
             mask[a:b] = True
         lo, hi = self._range[path]
@@ -375,10 +399,18 @@ class Corpus:
         cache = self.__dict__.setdefault("_import_words_cache", {})
         words = cache.get(path)
         if words is None or len(words) != (len(self.all_premises) + 31) // 32:
+            # files are contiguous in all_premises: expand the file-level bit set by the file sizes
+            sizes = cache.get(None)
+            if sizes is None or len(sizes) != len(self._order):
+                sizes = np.fromiter((len(self._files[p].premises) for p in self._order), dtype=np.int64,
+                                    count=len(self._order))
+                cache.clear()
+                cache[None] = sizes
+            nbytes = (len(self._order) + 7) // 8
+            file_bits = np.unpackbits(np.frombuffer(self._dep_bits[path].to_bytes(nbytes, "little"), dtype=np.uint8),
+                                      bitorder="little")[: len(self._order)].astype(bool)
             mask = np.zeros((len(self.all_premises) + 31) // 32 * 32, dtype=bool)
-            for dep in self._deps[path]:
-                a, b = self._range[dep]
-                mask[a:b] = True
+            mask[: len(self.all_premises)] = np.repeat(file_bits, sizes)
             words = np.packbits(mask.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view("<u4").copy()
             cache[path] = words
         return words

@@ -408,3 +408,47 @@ def test_encode_texts_groups_by_token_budget_and_keeps_row_order():
     before = r.corpus_embeddings
     r.reindex_corpus(batch_size=4)             # fresh index: no-op (reference :185-186)
     assert r.corpus_embeddings is before
+
+
+def test_import_closure_bitsets_and_old_pickles():
+    """Transitive imports are kept as bit sets over the file order; a corpus pickled with the earlier
+    representation (sets of paths under `_deps`) is upgraded on load and answers identically."""
+    rng = np.random.default_rng(5)
+    files = []
+    for f in range(60):
+        imports = sorted({f"S/F{int(i)}.lean" for i in rng.integers(0, f, size=min(f, 3))}) if f else []
+        prem = [Premise(f"S/F{f}.lean", f"S.F{f}.l{j}", Pos(10 * j + 1, 0), Pos(10 * j + 5, 0), f"theorem l{j} : True")
+                for j in range(int(rng.integers(1, 6)))]
+        files.append((File(f"S/F{f}.lean", prem), imports))
+    c = Corpus.from_files(files)
+    # closure by definition
+    direct = {f.path: set(imps) for f, imps in files}
+    def closure(p, seen=None):
+        seen = set() if seen is None else seen
+        for d in direct[p]:
+            if d not in seen:
+                seen.add(d)
+                closure(d, seen)
+        return seen
+    order = [f.path for f, _ in files]
+    for p in order:
+        assert c.get_dependencies(p) == [q for q in order if q in closure(p)]
+    # masks: packed words == boolean mask == membership in the reference-style accessible set
+    for p in (order[0], order[17], order[-1]):
+        pos = Pos(25, 0)
+        b = c.accessible_mask(p, pos)
+        w = c.accessible_mask_words(p, pos)
+        assert (np.unpackbits(w.view(np.uint8), bitorder="little")[: len(c)].astype(bool) == b).all()
+        acc = c.get_accessible_premises(p, pos)
+        assert [q in acc for q in c.all_premises] == b.tolist()
+    # old-format state
+    state = c.__getstate__()
+    old = {k: v for k, v in state.items() if k not in ("_order", "_index", "_dep_bits")}
+    old["_deps"] = {p: frozenset(closure(p)) for p in order}
+    c_old = Corpus.__new__(Corpus)
+    c_old.__setstate__(old)
+    for p in (order[3], order[-1]):
+        assert c_old.get_dependencies(p) == c.get_dependencies(p)
+        assert (c_old.accessible_mask_words(p, Pos(99, 0)) == c.accessible_mask_words(p, Pos(99, 0))).all()
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2.get_dependencies(order[-1]) == c.get_dependencies(order[-1])
