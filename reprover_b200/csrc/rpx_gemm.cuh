@@ -350,9 +350,9 @@ struct EpiStoreBF16 {
 // 128-byte lines.  Each warp therefore transposes its 32x32 fp32 block through a swizzled
 // shared-memory tile and does the read-modify-write with lanes running along the row:
 // one instruction covers 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32).
-// Residual loads run one chunk ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting the chunks — was measured
-// neutral to slightly negative on B200 and is off by default.)
-// (Measured and dropped: an L2 prefetch of the next tile's residual rows one tile ahead — the lines
+// Residual loads run one chunk ahead.  (RPX_EPI_WARPS=8 — two warps per TMEM lane group splitting
+// the chunks — was measured neutral to slightly negative on B200 and is off by default.  Measured
+// and dropped: an L2 prefetch of the next tile's residual rows one tile ahead — the lines
 // were evicted again before use, 6.0 GB read per launch against 3.4 GB algorithmic — and L2
 // eviction-priority hints on the residual loads / stores, 0 %.)
 struct EpiResidual {
@@ -360,7 +360,7 @@ struct EpiResidual {
     float* h32;
     __nv_bfloat16* h16;
     int ld;
-    float* ss_out;  // [tiles_n * 2][ss_stride]
+    float* ss_out;  // [tiles_n * kWarps / 4][ss_stride]
     int ss_stride;
   };
   static constexpr int kWarps = RPX_EPI_WARPS;
