@@ -10,15 +10,22 @@ CPU restatement of the reference's premise-retrieval hot path, function by funct
     get_nearest_premises()   <- Corpus.get_nearest_premises        common.py:299-326
     retrieve()               <- PremiseRetriever.retrieve          retrieval/model.py:338-375
 
-The reference modules themselves cannot be imported (`lean_dojo`, `pytorch_lightning`,
-`deepspeed` are not installed), but the arithmetic they delegate to is
-third-party code that IS installed and is used here directly:
-`transformers.T5EncoderModel` / `ByT5Tokenizer` (transformers 5.5.0; the reference pins
-no version) and `torch` (2.11).  The reference has no tests or golden vectors for this
-path, so **parity is pinned by running that third-party code itself**:
-the encoder oracle *is* HF's `T5EncoderModel` in fp32 with
-`torch.set_float32_matmul_precision("highest")`; golden fixtures generated from it are in
-`tests/golden/` (script: `tests/golden/make_golden.py`).
+Pinning.  The reference has no tests or golden vectors for this path.  This
+restatement is therefore pinned against OUTPUTS OF THE REFERENCE'S OWN CODE, generated in the build
+container and committed under `tests/golden/` together with the generating scripts:
+
+  * `make_reference_retriever_golden.py` imports `/root/reference/retrieval/model.py` + `common.py`
+    unmodified (the three missing packages — lean_dojo, pytorch_lightning, deepspeed — are stubbed;
+    the stubs contribute `Pos` and a LightningModule base, nothing else) and records
+    `PremiseRetriever.reindex_corpus / _encode / retrieve` on a synthetic ByT5-small checkpoint;
+  * `make_reference_goldens.py` records the host data model (`Premise.serialize`, `Corpus`,
+    accessibility, `get_nearest_premises`).
+
+`tests/test_oracle_cpu.py` replays both against this module (embeddings to 5e-6, identical premises /
+order / scores / ValueError).  The arithmetic itself is third-party code that is installed and used
+here directly — `transformers.T5EncoderModel` / `ByT5Tokenizer` (transformers 5.5.0; the reference pins
+no version) and `torch` (2.11) — and is additionally pinned by `tests/golden/make_golden.py`
+(bucket table, tokenizer probes, BASELINE config-1 embeddings).
 
 Deviation that is a deterministic refinement, not a change: ranking uses a stable
 descending sort on fp64 scores (ties -> lower index first) where the reference's

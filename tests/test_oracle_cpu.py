@@ -132,3 +132,109 @@ def test_oracle_encode_is_padding_invariant():
     a = ref.reindex_corpus(enc, tok, texts, 5, 64)
     b = ref.reindex_corpus(enc, tok, texts, 1, 64)
     assert torch.allclose(a, b, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# Goldens produced by the reference's own code (tests/golden/make_reference_goldens.py imports
+# /root/reference/common.py unmodified): Premise.serialize, File.from_data filtering, corpus order,
+# transitive imports, accessibility, locate_premise, get_nearest_premises (CPU fp32).
+
+def _reference_host_golden():
+    return json.loads((GOLD / "reference_host_model.json").read_text())
+
+
+def _our_corpus_from_golden(g, tmp_path):
+    from reprover_b200.corpus import Corpus
+    jsonl = tmp_path / "corpus.jsonl"
+    jsonl.write_text("\n".join(json.dumps(l) for l in g["corpus_lines"]))
+    return Corpus(str(jsonl))
+
+
+def test_host_model_matches_goldens_from_the_reference_code(tmp_path):
+    from reprover_b200.corpus import Pos
+    g = _reference_host_golden()
+    c = _our_corpus_from_golden(g, tmp_path)
+    # File.from_data filtering + corpus order
+    assert [[p.path, p.full_name, [p.start.line_nb, p.start.column_nb], [p.end.line_nb, p.end.column_nb]]
+            for p in c.all_premises] == g["all_premises"]
+    # Premise.serialize (the fast path and the regex path both occur in this corpus)
+    assert [p.serialize() for p in c.all_premises] == g["serialize"]
+    assert any("<a>" in s for s in g["serialize"]) and any("<a>" not in s for s in g["serialize"])
+    # transitive imports (the reference returns them in graph order: compare as sets)
+    for path, deps in g["dependencies"].items():
+        assert sorted(c.get_dependencies(path)) == deps
+        assert c.num_premises(path) == g["num_premises"][path]
+    # accessibility at a position, three ways: boolean mask, packed words, PremiseSet membership
+    for ctx in g["contexts"]:
+        pos = Pos(*ctx["pos"])
+        want = ctx["member_of_accessible_set"]
+        assert ctx["accessible_indexes"] == want        # (no divergence between the two reference notions here)
+        mask = c.accessible_mask(ctx["path"], pos)
+        assert np.flatnonzero(mask).tolist() == want
+        words = c.accessible_mask_words(ctx["path"], pos)
+        assert np.flatnonzero(np.unpackbits(words.view(np.uint8), bitorder="little")[: len(c)]).tolist() == want
+        acc = c.get_accessible_premises(ctx["path"], pos)
+        assert [i for i, p in enumerate(c.all_premises) if p in acc] == want
+        located = c.locate_premise(ctx["path"], pos)
+        assert (None if located is None else c.all_premises.index(located)) == ctx["located"]
+
+
+def test_oracle_nearest_premises_matches_goldens_from_the_reference_code(tmp_path):
+    """`oracle/reference_path.py::get_nearest_premises` (the checker of every retrieval parity test)
+    against what the reference's `Corpus.get_nearest_premises` returned for the same fp32 inputs:
+    same premises in the same order, same scores, ValueError for the same contexts."""
+    from reprover_b200.corpus import Context, Pos
+    g = _reference_host_golden()
+    c = _our_corpus_from_golden(g, tmp_path)
+    near = g["nearest"]
+    E = torch.tensor(near["E"], dtype=torch.float32)
+    Q = torch.tensor(near["Q"], dtype=torch.float32)
+    raised = 0
+    for j, (ctx, want) in enumerate(zip(g["contexts"], near["results"])):
+        context = Context(ctx["path"], "Gold.some_theorem", Pos(*ctx["pos"]), "h : p\n⊢ q")
+        if "raises" in want:
+            with pytest.raises(ValueError):
+                ref.get_nearest_premises(c, E, [context], Q[j:j + 1], near["k"])
+            raised += 1
+            continue
+        prem, scores = ref.get_nearest_premises(c, E, [context], Q[j:j + 1], near["k"])
+        assert [c.all_premises.index(p) for p in prem[0]] == want["indices"]
+        assert np.allclose(scores[0], want["scores"], atol=1e-6)
+    assert 0 < raised < len(near["results"])
+
+
+def test_oracle_matches_goldens_from_the_reference_retriever(tmp_path):
+    """`tests/golden/reference_retriever_cfg1.*` holds what the reference's own `PremiseRetriever`
+    (retrieval/model.py, imported unmodified by tests/golden/make_reference_retriever_golden.py) returned
+    on the CPU for `reindex_corpus`, `_encode` and `retrieve` on a synthetic ByT5-small checkpoint.  The
+    oracle — the checker of every GPU parity test — must reproduce it: embeddings to fp32 round-off,
+    the same premises in the same order, the same scores, ValueError in the same place."""
+    from reprover_b200.corpus import Context, Pos
+    meta = json.loads((GOLD / "reference_retriever_cfg1.json").read_text())
+    g = np.load(GOLD / "reference_retriever_cfg1.npz")
+    cfg = dict(synth.BYT5_SMALL)
+    sd = synth.random_t5_state_dict(cfg, seed=meta["weight_seed"])
+    torch.set_float32_matmul_precision("highest")
+    enc, tok = ref.build_hf_encoder(cfg, sd), ref.build_hf_tokenizer()
+    corpus = _our_corpus_from_golden(meta, tmp_path)
+    texts = [p.serialize() for p in corpus.all_premises]
+    assert all("<a>" in t for t in texts)
+    # reindex_corpus (reference :183-210)
+    emb = ref.reindex_corpus(enc, tok, texts, meta["reindex_batch_size"], meta["max_seq_len"])
+    np.testing.assert_allclose(emb.numpy(), g["corpus_embeddings"], rtol=0, atol=5e-6)
+    # _encode on the recorded padded batch (reference :92-114), and the tokenizer call that made it
+    ids, mask = torch.from_numpy(g["state_input_ids"]), torch.from_numpy(g["state_attention_mask"])
+    t = ref.tokenize(tok, meta["states"], meta["max_seq_len"])
+    assert torch.equal(t.input_ids, ids) and torch.equal(t.attention_mask, mask)
+    np.testing.assert_allclose(ref.encode(enc, ids, mask).numpy(), g["state_embeddings"], rtol=0, atol=5e-6)
+    # retrieve (reference :338-375)
+    for q in meta["queries"]:
+        ctx = Context(q["path"], "Gold.target", Pos(*q["pos"]), q["state"])
+        prem, scores = ref.retrieve(enc, tok, corpus, emb, ctx, q["k"], meta["max_seq_len"])
+        assert [[p.path, p.full_name] for p in prem] == q["retrieved"]
+        assert np.allclose(scores, q["scores"], atol=1e-5)
+    few = meta["too_few_accessible"]
+    assert few["raised_value_error"]
+    with pytest.raises(ValueError):
+        ref.retrieve(enc, tok, corpus, emb, Context(few["path"], "Gold.target", Pos(*few["pos"]), meta["states"][few["state"]]),
+                     few["k"], meta["max_seq_len"])
