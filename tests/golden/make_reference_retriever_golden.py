@@ -14,8 +14,9 @@ they are replaced by stubs.  What the exercised code needs from them is stated h
 it is the only code on this path that is not the reference's (or HF's) own:
   * `lean_dojo.Pos` — 2-int ordered, hashable dataclass (line_nb, column_nb);
   * `pytorch_lightning.LightningModule` — a `torch.nn.Module` with `save_hyperparameters()` (no-op),
-    `.device` / `.dtype` (of the first parameter) and `.trainer` raising RuntimeError when the module is not
-    attached to a trainer (Lightning's behaviour; it makes `cpu_checkpointing_enabled` return False);
+    `.device` / `.dtype` (of the first parameter), `.trainer` raising RuntimeError when the module is not
+    attached to a trainer (Lightning's behaviour; it makes `cpu_checkpointing_enabled` return False) and
+    `.log(name, value, **kw)` recording the metric;
   * `DeepSpeedStrategy`, `FusedAdam`, ... — names only.
 The module sets `torch.set_float32_matmul_precision("medium")` at import (retrieval/model.py:26), which on
 AMX hosts rounds fp32 matmuls through bf16; the fixture is generated under "highest" so that it pins the
@@ -70,6 +71,9 @@ def _stub_modules():
         @property
         def trainer(self):
             raise RuntimeError("not attached to a Trainer")
+
+        def log(self, name, value, **kw):   # Lightning's metric sink: record what the step reports
+            self.__dict__.setdefault("logged", {})[name] = {"value": float(value), "batch_size": kw.get("batch_size")}
 
     def mod(name, **attrs):
         m = types.ModuleType(name)
@@ -153,12 +157,43 @@ def main():
         except ValueError:
             raised = True
 
+        # validation_step / predict_step (reference :215-268, :281-327) on a batch of three contexts
+        retr.num_retrieved = 3
+        by_name = {p.full_name: p for p in retr.corpus.all_premises}
+        vctx = [refc.Context("Gold/F1.lean", "Gold.t0", Pos(30, 0), states[0]),
+                refc.Context("Gold/F1.lean", "Gold.t1", Pos(8, 0), states[1]),
+                refc.Context("Gold/F0.lean", "Gold.t2", Pos(49, 0), states[0])]
+        positives = [["Gold.F0.lemma_2", "Gold.F1.lemma_1"], [], ["Gold.F0.lemma_4"]]
+        vtok = retr.tokenizer([c.serialize() for c in vctx], padding="longest", max_length=512, truncation=True,
+                              return_tensors="pt")
+        batch = {"context": vctx, "context_ids": vtok.input_ids, "context_mask": vtok.attention_mask,
+                 "all_pos_premises": [[by_name[n] for n in names] for names in positives],
+                 "url": ["u0", "u1", "u2"], "commit": ["c0", "c1", "c2"], "file_path": [c.path for c in vctx],
+                 "full_name": [c.theorem_full_name for c in vctx], "start": [list(c.theorem_pos) for c in vctx],
+                 "tactic_idx": [0, 1, 2]}
+        with torch.no_grad():
+            retr.validation_step(batch, 0)
+            retr.predict_step_outputs = []
+            retr.predict_step(batch, 0)
+        validation = {
+            "num_retrieved": 3,
+            "contexts": [{"path": c.path, "theorem_full_name": c.theorem_full_name, "pos": list(c.theorem_pos), "state": c.state}
+                         for c in vctx],
+            "all_pos_premises": positives,
+            "logged": retr.logged,
+            "predictions": [{"url": r["url"], "commit": r["commit"], "file_path": r["file_path"], "full_name": r["full_name"],
+                             "start": r["start"], "tactic_idx": r["tactic_idx"],
+                             "retrieved_premises": [p.full_name for p in r["retrieved_premises"]], "scores": r["scores"]}
+                            for r in retr.predict_step_outputs],
+        }
+
     np.savez_compressed(OUT_NPZ, corpus_embeddings=corpus_emb, state_embeddings=state_emb,
                         state_input_ids=tok.input_ids.numpy(), state_attention_mask=tok.attention_mask.numpy())
     OUT_JSON.write_text(json.dumps({
         "generator": "tests/golden/make_reference_retriever_golden.py (reference retrieval/model.py + common.py imported unmodified; see its docstring)",
         "weight_seed": synth.SEED, "max_seq_len": 512, "reindex_batch_size": 3,
         "corpus_lines": lines, "states": states, "queries": queries,
+        "validation": validation,
         "too_few_accessible": {"state": 0, "path": "Gold/F0.lean", "pos": [7, 0], "k": 2, "raised_value_error": raised},
     }, indent=1, ensure_ascii=False))
     print("wrote", OUT_NPZ.name, corpus_emb.shape, state_emb.shape, "and", OUT_JSON.name)

@@ -233,6 +233,23 @@ def test_oracle_matches_goldens_from_the_reference_retriever(tmp_path):
         prem, scores = ref.retrieve(enc, tok, corpus, emb, ctx, q["k"], meta["max_seq_len"])
         assert [[p.path, p.full_name] for p in prem] == q["retrieved"]
         assert np.allclose(scores, q["scores"], atol=1e-5)
+    # validation_step / predict_step (reference :215-268, :281-327): batched retrieval + Recall@k / MRR
+    from reprover_b200.evaluation import recall_and_mrr
+    val = meta["validation"]
+    by_name = {p.full_name: p for p in corpus.all_premises}
+    vctx = [Context(c["path"], c["theorem_full_name"], Pos(*c["pos"]), c["state"]) for c in val["contexts"]]
+    vtok = ref.tokenize(tok, [c.serialize() for c in vctx], meta["max_seq_len"])
+    vemb = ref.encode(enc, vtok.input_ids, vtok.attention_mask)
+    prem, scores = ref.get_nearest_premises(corpus, emb, vctx, vemb, val["num_retrieved"])
+    for got_p, got_s, want in zip(prem, scores, val["predictions"]):
+        assert [p.full_name for p in got_p] == want["retrieved_premises"]
+        assert np.allclose(got_s, want["scores"], atol=1e-5)
+    positives = [[by_name[n] for n in names] for names in val["all_pos_premises"]]
+    recall, mrr, n_with = recall_and_mrr(positives, prem, val["num_retrieved"])
+    for j in range(val["num_retrieved"]):
+        logged = val["logged"][f"Recall@{j + 1}_val"]
+        assert recall[j] == pytest.approx(logged["value"]) and logged["batch_size"] == n_with
+    assert mrr == pytest.approx(val["logged"]["MRR"]["value"])
     few = meta["too_few_accessible"]
     assert few["raised_value_error"]
     with pytest.raises(ValueError):
