@@ -5,7 +5,9 @@
 Imports `/root/reference/retrieval/model.py` and `/root/reference/common.py` unmodified, builds the
 reference retriever with `PremiseRetriever.load_hf(<synthetic ByT5-small checkpoint>, 512, "cpu")`,
 attaches a small synthetic corpus (`load_corpus(jsonl)`), and records what the reference's own
-`reindex_corpus(batch_size)`, `_encode(ids, mask)` and `retrieve(state, file, theorem, pos, k)` return.
+`reindex_corpus(batch_size)`, `_encode(ids, mask)`, `retrieve(state, file, theorem, pos, k)`,
+`validation_step` / `predict_step` return, plus the pickled `IndexedCorpus` that `retrieval/index.py:37-40`
+writes (`reference_indexed_corpus.pickle`: classes `common.*`, `lean_dojo.Pos`, a networkx graph).
 `tests/test_oracle_cpu.py` replays the committed fixture against `oracle/reference_path.py`, which the
 GPU parity tests in turn use as their checker.
 
@@ -38,6 +40,7 @@ from reprover_b200 import synth  # noqa: E402  (synthetic checkpoint + premise s
 
 OUT_NPZ = HERE / "reference_retriever_cfg1.npz"
 OUT_JSON = HERE / "reference_retriever_cfg1.json"
+OUT_PICKLE = HERE / "reference_indexed_corpus.pickle"
 
 
 def _stub_modules():
@@ -55,6 +58,8 @@ def _stub_modules():
 
         def __le__(self, other):
             return (self.line_nb, self.column_nb) <= (other.line_nb, other.column_nb)
+
+    Pos.__module__, Pos.__qualname__ = "lean_dojo", "Pos"   # pickles as lean_dojo.Pos, like the real class
 
     class LightningModule(torch.nn.Module):
         def save_hyperparameters(self, *a, **k):
@@ -156,6 +161,11 @@ def main():
             raised = False
         except ValueError:
             raised = True
+
+        # the on-disk index exactly as retrieval/index.py:37-40 writes it
+        import pickle
+        OUT_PICKLE.write_bytes(pickle.dumps(
+            refc.IndexedCorpus(retr.corpus, retr.corpus_embeddings.to(torch.float32).cpu())))
 
         # validation_step / predict_step (reference :215-268, :281-327) on a batch of three contexts
         retr.num_retrieved = 3

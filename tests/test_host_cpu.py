@@ -452,3 +452,30 @@ def test_import_closure_bitsets_and_old_pickles():
         assert (c_old.accessible_mask_words(p, Pos(99, 0)) == c.accessible_mask_words(p, Pos(99, 0))).all()
     c2 = pickle.loads(pickle.dumps(c))
     assert c2.get_dependencies(order[-1]) == c.get_dependencies(order[-1])
+
+
+def test_index_written_by_the_reference_code_loads(tmp_path):
+    """`tests/golden/reference_indexed_corpus.pickle` was written by the reference's own classes
+    (`common.IndexedCorpus(corpus, embeddings.float().cpu())`, retrieval/index.py:37-40; generator:
+    tests/golden/make_reference_retriever_golden.py).  `load_corpus(path)` must accept it without
+    `common` / `lean_dojo` being importable and end up with the same corpus and embeddings."""
+    gold = Path(__file__).resolve().parent / "golden"
+    meta = json.loads((gold / "reference_retriever_cfg1.json").read_text())
+    want_emb = np.load(gold / "reference_retriever_cfg1.npz")["corpus_embeddings"]
+    r = _stub_retriever(10**9)
+    r.load_corpus(str(gold / "reference_indexed_corpus.pickle"))
+    assert not r.embeddings_staled
+    assert r.corpus_embeddings.dtype == torch.float32 and r.corpus_embeddings.device.type == "cpu"
+    assert np.array_equal(r.corpus_embeddings.numpy(), want_emb)
+    want = [(l["path"], p["full_name"], p["code"], tuple(p["start"]), tuple(p["end"]))
+            for l in meta["corpus_lines"] for p in l["premises"]]
+    got = [(p.path, p.full_name, p.code, (p.start.line_nb, p.start.column_nb), (p.end.line_nb, p.end.column_nb))
+           for p in r.corpus.all_premises]
+    assert got == want
+    assert r.corpus.get_dependencies("Gold/F1.lean") == ["Gold/F0.lean"] and r.corpus.get_dependencies("Gold/F0.lean") == []
+    # the converted corpus answers accessibility like one built from the jsonl
+    jsonl = tmp_path / "corpus.jsonl"
+    jsonl.write_text("\n".join(json.dumps(l) for l in meta["corpus_lines"]))
+    fresh = Corpus(str(jsonl))
+    for path, pos in [("Gold/F1.lean", Pos(8, 0)), ("Gold/F0.lean", Pos(27, 0)), ("Gold/F1.lean", Pos(999, 0))]:
+        assert (r.corpus.accessible_mask_words(path, pos) == fresh.accessible_mask_words(path, pos)).all()
