@@ -40,8 +40,13 @@ class Pos:
             return p
         if hasattr(p, "line_nb") and hasattr(p, "column_nb"):
             return cls(int(p.line_nb), int(p.column_nb))
-        a, b = p
-        return cls(int(a), int(b))
+        # the reference asserts isinstance(pos, lean_dojo.Pos): anything that is not position-like
+        # fails the same way (AssertionError), not with whatever unpacking happens to raise
+        try:
+            a, b = p
+            return cls(int(a), int(b))
+        except (TypeError, ValueError):
+            raise AssertionError(f"not a source position: {p!r}") from None
 
     def _key(self) -> Tuple[int, int]:
         return (self.line_nb, self.column_nb)

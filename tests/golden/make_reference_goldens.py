@@ -154,6 +154,56 @@ def main():
         except ValueError:
             nearest["results"].append({"raises": "ValueError"})
     out["nearest"] = nearest
+    # constructor invariants (AssertionError or not) and PremiseSet / equality / hashing semantics
+    def outcome(fn):
+        try:
+            fn()
+            return "ok"
+        except AssertionError:
+            return "AssertionError"
+        except Exception as e:  # anything else the reference lets through
+            return type(e).__name__
+
+    ctor_cases = [
+        ["Context", ["A.lean", "A.t", [1, 0], "h : p\n⊢ q"]],
+        ["Context", ["A.lean", "A.t", [1, 0], "no turnstile"]],
+        ["Context", ["A.lean", "A.t", [1, 0], "⊢ <a>x</a>"]],
+        ["Context", ["A.lean", "A.t", [1, 0], "⊢ x </a>"]],
+        ["Context", [7, "A.t", [1, 0], "⊢ q"]],
+        ["Context", ["A.lean", None, [1, 0], "⊢ q"]],
+        ["Context", ["A.lean", "A.t", None, "⊢ q"]],
+        ["Premise", ["A.lean", "A.x", [1, 0], [2, 0], "def x := 1"]],
+        ["Premise", ["A.lean", "A.x", [2, 0], [2, 0], "def x := 1"]],
+        ["Premise", ["A.lean", "A.x", [2, 1], [2, 0], "def x := 1"]],
+        ["Premise", ["A.lean", "A.x", [1, 0], [2, 0], ""]],
+        ["Premise", ["A.lean", "A.x", [1, 0], [2, 0], None]],
+        ["Premise", ["A.lean", 5, [1, 0], [2, 0], "def x := 1"]],
+        ["Premise", ["A.lean", "A.x", None, [2, 0], "def x := 1"]],
+    ]
+
+    def build(kind, a):
+        if kind == "Context":
+            return refc.Context(a[0], a[1], None if a[2] is None else Pos(*a[2]), a[3])
+        return refc.Premise(a[0], a[1], None if a[2] is None else Pos(*a[2]), None if a[3] is None else Pos(*a[3]), a[4])
+
+    out["constructors"] = [{"kind": k, "args": a, "outcome": outcome(lambda k=k, a=a: build(k, a))} for k, a in ctor_cases]
+
+    P = lambda path, name, s, e, code: refc.Premise(path, name, Pos(*s), Pos(*e), code)   # noqa: E731
+    a1 = P("A.lean", "A.x", (1, 0), (2, 0), "def x := 1")
+    a2 = P("A.lean", "A.x", (1, 0), (9, 9), "other code")        # end / code do not take part in ==
+    a3 = P("A.lean", "A.x", (5, 0), (6, 0), "def x := 1")        # start does
+    b1 = P("B.lean", "A.x", (1, 0), (2, 0), "def x := 1")
+    ps = refc.PremiseSet()
+    ps.update([a1, b1])
+    ps.add(a3)                                                   # same (path, full_name): replaces a1
+    out["premise_semantics"] = {
+        "a1==a2": a1 == a2, "a1==a3": a1 == a3, "hash(a1)==hash(a2)": hash(a1) == hash(a2),
+        "len": len(ps), "a1 in": a1 in ps, "a2 in": a2 in ps, "a3 in": a3 in ps, "b1 in": b1 in ps,
+        "iter": [[p.path, p.full_name, list(p.start)] for p in ps],
+        "remove_marks": refc.remove_marks("x <a>Nat.add</a> y </a><a>"),
+        "context_serialize": refc.Context("A.lean", "A.t", Pos(1, 0), "h : p\n⊢ q").serialize(),
+        "context_eq_ignores_pos": refc.Context("A.lean", "A.t", Pos(1, 0), "⊢ q") == refc.Context("A.lean", "A.t", Pos(9, 9), "⊢ q"),
+    }
     OUT.write_text(json.dumps(out, indent=1, ensure_ascii=False))
     print(f"wrote {OUT}: {n} premises, {len(contexts)} contexts")
 

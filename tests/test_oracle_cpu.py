@@ -255,3 +255,42 @@ def test_oracle_matches_goldens_from_the_reference_retriever(tmp_path):
     with pytest.raises(ValueError):
         ref.retrieve(enc, tok, corpus, emb, Context(few["path"], "Gold.target", Pos(*few["pos"]), meta["states"][few["state"]]),
                      few["k"], meta["max_seq_len"])
+
+
+def test_constructor_invariants_and_set_semantics_match_the_reference_code():
+    """Which `Context` / `Premise` constructions the reference accepts or rejects (AssertionError), what
+    takes part in `==` / `hash`, and how `PremiseSet` treats a repeated (path, full_name) — replayed
+    from `reference_host_model.json` (recorded from the reference's own classes)."""
+    from reprover_b200.corpus import Context, Pos, Premise, PremiseSet, remove_marks
+    g = _reference_host_golden()
+
+    def build(kind, a):
+        if kind == "Context":
+            return Context(a[0], a[1], None if a[2] is None else Pos(*a[2]), a[3])
+        return Premise(a[0], a[1], None if a[2] is None else Pos(*a[2]), None if a[3] is None else Pos(*a[3]), a[4])
+
+    for case in g["constructors"]:
+        try:
+            build(case["kind"], case["args"])
+            got = "ok"
+        except AssertionError:
+            got = "AssertionError"
+        assert got == case["outcome"], case
+    sem = g["premise_semantics"]
+    P = lambda path, name, s, e, code: Premise(path, name, Pos(*s), Pos(*e), code)   # noqa: E731
+    a1 = P("A.lean", "A.x", (1, 0), (2, 0), "def x := 1")
+    a2 = P("A.lean", "A.x", (1, 0), (9, 9), "other code")
+    a3 = P("A.lean", "A.x", (5, 0), (6, 0), "def x := 1")
+    b1 = P("B.lean", "A.x", (1, 0), (2, 0), "def x := 1")
+    ps = PremiseSet()
+    ps.update([a1, b1])
+    ps.add(a3)
+    got = {
+        "a1==a2": a1 == a2, "a1==a3": a1 == a3, "hash(a1)==hash(a2)": hash(a1) == hash(a2),
+        "len": len(ps), "a1 in": a1 in ps, "a2 in": a2 in ps, "a3 in": a3 in ps, "b1 in": b1 in ps,
+        "iter": [[p.path, p.full_name, [p.start.line_nb, p.start.column_nb]] for p in ps],
+        "remove_marks": remove_marks("x <a>Nat.add</a> y </a><a>"),
+        "context_serialize": Context("A.lean", "A.t", Pos(1, 0), "h : p\n⊢ q").serialize(),
+        "context_eq_ignores_pos": Context("A.lean", "A.t", Pos(1, 0), "⊢ q") == Context("A.lean", "A.t", Pos(9, 9), "⊢ q"),
+    }
+    assert got == sem
