@@ -169,6 +169,7 @@ def test_host_model_matches_goldens_from_the_reference_code(tmp_path):
         pos = Pos(*ctx["pos"])
         want = ctx["member_of_accessible_set"]
         assert ctx["accessible_indexes"] == want        # (no divergence between the two reference notions here)
+        assert c.get_accessible_premise_indexes(ctx["path"], pos) == ctx["accessible_indexes"]
         mask = c.accessible_mask(ctx["path"], pos)
         assert np.flatnonzero(mask).tolist() == want
         words = c.accessible_mask_words(ctx["path"], pos)
