@@ -204,6 +204,33 @@ def main():
         "context_serialize": refc.Context("A.lean", "A.t", Pos(1, 0), "h : p\n⊢ q").serialize(),
         "context_eq_ignores_pos": refc.Context("A.lean", "A.t", Pos(1, 0), "⊢ q") == refc.Context("A.lean", "A.t", Pos(9, 9), "⊢ q"),
     }
+    # Premise.serialize on adversarial (name, code) pairs: un-escaped dots, repeated / overlapping /
+    # adjacent occurrences, « » quoting, look-behind at string start and after newlines / NBSP, suffix
+    # fallback, names with regex metacharacters (some are invalid patterns: the exception type is recorded)
+    rng = np.random.default_rng(11)
+    comps = ["Nat", "add", "add_comm", "a", "ab", "foo'", "β", "x1", "comm", "a+b", "f(x", "x*", "[b]", "«q r»", "p.q"]
+    glue = [" ", "\n", "\t", ".", "x", "«", "»", "(", ":", "  ", "\u00a0", "_", "a", "Nat", "add", "comm", "ab", "β", "+", "*"]
+    ser_cases = []
+    for _ in range(400):
+        name = ".".join(comps[int(i)] for i in rng.integers(0, len(comps), int(rng.integers(1, 4))))
+        pieces = []
+        for _ in range(int(rng.integers(1, 12))):
+            r = rng.random()
+            if r < 0.35:
+                pieces.append(name if rng.random() < 0.5 else name.split(".", 1)[-1])
+            elif r < 0.5:
+                pieces.append(name.replace(".", glue[int(rng.integers(0, len(glue)))]))
+            elif r < 0.55:
+                pieces.append("_root_." + name)
+            else:
+                pieces.append(glue[int(rng.integers(0, len(glue)))])
+        code = "".join(pieces) or "x"
+        try:
+            res = {"out": refc.Premise("A.lean", name, Pos(1, 0), Pos(2, 0), code).serialize()}
+        except Exception as e:
+            res = {"raises": type(e).__name__}
+        ser_cases.append({"full_name": name, "code": code, **res})
+    out["serialize_cases"] = ser_cases
     OUT.write_text(json.dumps(out, indent=1, ensure_ascii=False))
     print(f"wrote {OUT}: {n} premises, {len(contexts)} contexts")
 

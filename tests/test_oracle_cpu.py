@@ -295,3 +295,23 @@ def test_constructor_invariants_and_set_semantics_match_the_reference_code():
         "context_eq_ignores_pos": Context("A.lean", "A.t", Pos(1, 0), "⊢ q") == Context("A.lean", "A.t", Pos(9, 9), "⊢ q"),
     }
     assert got == sem
+
+
+def test_premise_serialize_matches_the_reference_on_adversarial_names():
+    """400 (name, code) pairs run through the reference's own `Premise.serialize` (recorded in
+    `reference_host_model.json`): un-escaped dots, overlapping and adjacent occurrences, « » quoting,
+    the whitespace look-behind, `_root_.` spellings, names that are regex metacharacter soup (including
+    invalid patterns, where the reference raises)."""
+    import re
+    from reprover_b200.corpus import Pos, Premise
+    g = _reference_host_golden()
+    n_marked = 0
+    for case in g["serialize_cases"]:
+        p = Premise("A.lean", case["full_name"], Pos(1, 0), Pos(2, 0), case["code"])
+        if "raises" in case:
+            with pytest.raises(re.error if case["raises"] in ("error", "PatternError") else Exception):
+                p.serialize()
+        else:
+            assert p.serialize() == case["out"], case
+            n_marked += "<a>" in case["out"]
+    assert n_marked > 50
