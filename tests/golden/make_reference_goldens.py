@@ -154,6 +154,17 @@ def main():
         except ValueError:
             nearest["results"].append({"raises": "ValueError"})
     out["nearest"] = nearest
+    # the same search on bf16-valued embeddings (what the GPU path holds): pins the C oracle's
+    # `rpx_oracle_sim_topk` (bf16 operands, fp64 accumulation, accessibility bitmask) to the reference walk
+    E16, Q16 = E.bfloat16().float(), Q.bfloat16().float()
+    nearest16 = {"k": k, "results": []}
+    for j, ctx in enumerate(ctxs):
+        try:
+            prem, scores = corpus.get_nearest_premises(E16, [ctx], Q16[j:j + 1], k)
+            nearest16["results"].append({"indices": [index_of[id(p)] for p in prem[0]], "scores": scores[0]})
+        except ValueError:
+            nearest16["results"].append({"raises": "ValueError"})
+    out["nearest_bf16"] = nearest16
     # constructor invariants (AssertionError or not) and PremiseSet / equality / hashing semantics
     def outcome(fn):
         try:

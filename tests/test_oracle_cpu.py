@@ -315,3 +315,25 @@ def test_premise_serialize_matches_the_reference_on_adversarial_names():
             assert p.serialize() == case["out"], case
             n_marked += "<a>" in case["out"]
     assert n_marked > 50
+
+
+def test_c_oracle_topk_matches_the_reference_walk_on_bf16_embeddings(tmp_path):
+    """`rpx_oracle_sim_topk` — the checker of every GPU retrieval test — against the reference's own
+    `Corpus.get_nearest_premises` on the same bf16-valued embeddings, with the accessibility of each
+    context applied as the packed bitmask the engine takes."""
+    from reprover_b200.corpus import Pos
+    g = _reference_host_golden()
+    c = _our_corpus_from_golden(g, tmp_path)
+    near, near16 = g["nearest"], g["nearest_bf16"]
+    E = torch.tensor(near["E"], dtype=torch.float32).bfloat16()
+    Q = torch.tensor(near["Q"], dtype=torch.float32).bfloat16()
+    k = near16["k"]
+    words = np.stack([c.accessible_mask_words(ctx["path"], Pos(*ctx["pos"])) for ctx in g["contexts"]])
+    scores, idx, count = c_oracle.sim_topk(c_oracle.bf16_bits(Q), c_oracle.bf16_bits(E), k, words)
+    for j, want in enumerate(near16["results"]):
+        if "raises" in want:
+            assert count[j] < k        # what the host turns into ValueError (common.py:323-324)
+            continue
+        assert count[j] == k
+        assert idx[j].tolist() == want["indices"]
+        assert np.allclose(scores[j], want["scores"], atol=1e-6)
