@@ -13,7 +13,10 @@ layout) can be exercised on CPU with the `gloo` backend and the oracle as stand-
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+import json
+import os
+import pickle
+from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -89,3 +92,78 @@ class ShardedIndex:
     def topk(self, queries: torch.Tensor, k: int, access_mask: Optional[torch.Tensor] = None, **kw):
         assert self.embeddings is not None
         return sharded_topk(queries, self.embeddings, k, self.lo, access_mask=access_mask, **kw)
+
+    # ------------------------------------------------------------------ on-disk form
+    # A directory: `manifest.json` (row bounds, dtype, width), one `embeddings.<r>-of-<R>.pt` per
+    # rank (its rows, in the dtype it holds them in) and, optionally, `corpus.pickle`.  Every rank
+    # writes and reads only its own rows; a directory written by R ranks can be read by any other
+    # number of ranks (rows are re-cut from the files that overlap the new range).  The single-file
+    # format the reference's prover loads (`IndexedCorpus` pickle, retrieval/index.py:37-40) is
+    # produced by `gather_indexed_corpus`.
+    @staticmethod
+    def _shard_file(directory: str, r: int, world: int) -> str:
+        return os.path.join(directory, f"embeddings.{r:05d}-of-{world:05d}.pt")
+
+    def save(self, directory: str, corpus: Any = None, group=None) -> None:
+        assert self.embeddings is not None
+        os.makedirs(directory, exist_ok=True)
+        torch.save(self.embeddings.detach().cpu().contiguous(), self._shard_file(directory, self.rank, self.world_size))
+        if self.rank == 0:
+            with open(os.path.join(directory, "manifest.json"), "w") as fh:
+                json.dump({"format": "reprover_b200.sharded_index/1", "n_rows_total": self.bounds[-1],
+                           "world_size": self.world_size, "bounds": self.bounds, "width": int(self.embeddings.shape[1]),
+                           "dtype": str(self.embeddings.dtype).replace("torch.", ""),
+                           "has_corpus": corpus is not None}, fh, indent=1)
+            if corpus is not None:
+                with open(os.path.join(directory, "corpus.pickle"), "wb") as fh:
+                    pickle.dump(corpus, fh)
+        if dist.is_initialized() and self.world_size > 1:
+            dist.barrier(group=group)   # the directory is complete when any rank returns
+
+    @classmethod
+    def load(cls, directory: str, rank: Optional[int] = None, world_size: Optional[int] = None,
+             device: Any = None) -> "ShardedIndex":
+        with open(os.path.join(directory, "manifest.json")) as fh:
+            man = json.load(fh)
+        assert man.get("format") == "reprover_b200.sharded_index/1", "not a sharded index directory"
+        index = cls(man["n_rows_total"], rank=rank, world_size=world_size)
+        parts = []
+        for r in range(man["world_size"]):
+            lo, hi = man["bounds"][r], man["bounds"][r + 1]
+            a, b = max(lo, index.lo), min(hi, index.hi)
+            if a >= b:
+                continue
+            rows = torch.load(cls._shard_file(directory, r, man["world_size"]), map_location="cpu", weights_only=True)
+            assert rows.shape == (hi - lo, man["width"]), f"shard {r} has shape {tuple(rows.shape)}"
+            parts.append(rows[a - lo:b - lo])
+        emb = torch.cat(parts) if parts else torch.empty(0, man["width"], dtype=getattr(torch, man["dtype"]))
+        index.set_embeddings(emb.to(device) if device is not None else emb)
+        return index
+
+    @staticmethod
+    def load_corpus(directory: str) -> Any:
+        with open(os.path.join(directory, "corpus.pickle"), "rb") as fh:
+            return pickle.load(fh)
+
+    def gather_embeddings(self, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+        """All rows, in order, as an fp32 CPU tensor on rank `dst` (None elsewhere)."""
+        assert self.embeddings is not None
+        if self.world_size == 1:
+            return self.embeddings.detach().to(torch.float32).cpu()
+        # equal-sized buffers for the collective: pad every shard to the longest one
+        longest = max(self.bounds[r + 1] - self.bounds[r] for r in range(self.world_size))
+        buf = torch.zeros(longest, self.embeddings.shape[1], dtype=self.embeddings.dtype, device=self.embeddings.device)
+        buf[: self.hi - self.lo] = self.embeddings
+        out = torch.empty((self.world_size * longest, buf.shape[1]), dtype=buf.dtype, device=buf.device)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        if self.rank != dst:
+            return None
+        out = out.view(self.world_size, longest, -1)
+        return torch.cat([out[r, : self.bounds[r + 1] - self.bounds[r]] for r in range(self.world_size)]).to(torch.float32).cpu()
+
+    def gather_indexed_corpus(self, corpus: Any, dst: int = 0, group=None):
+        """The reference's on-disk object (`IndexedCorpus(corpus, fp32 CPU embeddings)`) on rank `dst`."""
+        from .corpus import IndexedCorpus
+
+        emb = self.gather_embeddings(dst=dst, group=group)
+        return None if emb is None else IndexedCorpus(corpus, emb)

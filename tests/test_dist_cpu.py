@@ -71,3 +71,57 @@ def test_single_process_path_needs_no_process_group():
     s32, idx, cnt, s64 = sharded_topk(Q, E, 4, 0, local_topk=_oracle_local_topk, merge=_oracle_merge)
     ws, wi, wc = c_oracle.sim_topk(c_oracle.bf16_bits(Q), c_oracle.bf16_bits(E), 4)
     assert np.array_equal(idx.numpy(), wi)
+
+
+def _disk_worker(rank, world, port, n_rows, directory, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        E = synth.random_unit_rows(n_rows, 64, seed=9, device="cpu")
+        index = ShardedIndex(n_rows)
+        index.set_embeddings(E[index.lo:index.hi].clone())
+        index.save(directory, corpus={"stand-in": "corpus"} if rank == 0 else None)
+        again = ShardedIndex.load(directory)                 # same world size: own file only
+        ok_same = torch.equal(again.embeddings, index.embeddings)
+        full = index.gather_embeddings(dst=0)
+        ic = None
+        if rank == 0:
+            from reprover_b200.corpus import Corpus, File, Pos, Premise
+            prem = [Premise("A.lean", f"A.p{i}", Pos(i + 1, 0), Pos(i + 1, 1), "c") for i in range(n_rows)]
+            ic = index.gather_indexed_corpus(Corpus.from_files([(File("A.lean", prem), [])]))
+            ic = (len(ic.corpus), tuple(ic.embeddings.shape), str(ic.embeddings.dtype), str(ic.embeddings.device))
+        else:
+            index.gather_indexed_corpus(None)
+        out_q.put((rank, ok_same, None if full is None else torch.equal(full, E.float()), ic))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_index_on_disk_roundtrip_and_resharding(tmp_path):
+    """Two ranks write their rows; the directory reads back per rank, re-cut for 1 and 3 ranks, and
+    gathers into the reference's single-file object on rank 0."""
+    n_rows, directory = 101, str(tmp_path / "index")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_disk_worker, args=(r, 2, port, n_rows, directory, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in results)                         # same-world reload == what was saved
+    assert results[0][2] is True and results[1][2] is None    # gather: full matrix on rank 0 only
+    assert results[0][3] == (n_rows, (n_rows, 64), "torch.float32", "cpu")
+    E = synth.random_unit_rows(n_rows, 64, seed=9, device="cpu")
+    one = ShardedIndex.load(directory, rank=0, world_size=1)
+    assert torch.equal(one.embeddings, E) and one.embeddings.dtype == torch.bfloat16
+    got = torch.cat([ShardedIndex.load(directory, rank=r, world_size=3).embeddings for r in range(3)])
+    assert torch.equal(got, E)
+    assert [ShardedIndex.load(directory, rank=r, world_size=3).lo for r in range(3)] == shard_bounds(n_rows, 3)[:-1]
+    assert ShardedIndex.load_corpus(directory) == {"stand-in": "corpus"}
+    assert sorted(os.listdir(directory)) == ["corpus.pickle", "embeddings.00000-of-00002.pt", "embeddings.00001-of-00002.pt",
+                                             "manifest.json"]
