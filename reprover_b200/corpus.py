@@ -434,6 +434,16 @@ class Corpus:
                     words[i >> 5] |= np.uint32(1 << (i & 31))
         return words
 
+    def accessible_mask_words_range(self, path: str, pos: Any, lo: int, hi: int) -> np.ndarray:
+        """The bits [lo, hi) of `accessible_mask_words`, re-packed from bit 0: the bitmask a rank that owns
+        rows [lo, hi) of a row-sharded index hands to `rpx_sim_topk` (bit i <=> global row lo + i)."""
+        assert 0 <= lo <= hi <= len(self.all_premises)
+        words = self.accessible_mask_words(path, pos)
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[lo:hi]
+        padded = np.zeros((hi - lo + 31) // 32 * 32, dtype=np.uint8)
+        padded[: hi - lo] = bits
+        return np.packbits(padded.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view("<u4").copy()
+
     # ---- nearest-neighbour search (signature of reference common.py:299-305) ---------------
     def get_nearest_premises(self, premise_embeddings, batch_context: List[Context], batch_context_emb, k: int):
         """k accessible premises with the highest similarity for every context, best first.

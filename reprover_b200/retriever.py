@@ -195,6 +195,46 @@ class B200PremiseRetriever:
             self.corpus_embeddings = self.corpus_embeddings.to(torch.bfloat16)
         return self.corpus.get_nearest_premises(self.corpus_embeddings, ctxs, context_emb, k)
 
+    # ------------------------------------------------------------------ row-sharded index
+    # One process per GPU, `torch.distributed` initialised by the caller.  `reindex_corpus_sharded`
+    # encodes only this rank's rows (no communication); `retrieve_batch_sharded` needs the same
+    # states on every rank and returns the same answer on every rank: local fused sim+top-k under
+    # this rank's slice of the accessibility bitmask, one all-gather, device-side merge.
+    @torch.no_grad()
+    def reindex_corpus_sharded(self, batch_size: int = 64, group=None) -> "ShardedIndex":
+        from .dist import ShardedIndex
+
+        assert self.corpus is not None, "load_corpus first"
+        index = getattr(self, "sharded_index", None)
+        if index is not None and index.embeddings is not None and index.bounds[-1] == len(self.corpus):
+            return index
+        index = ShardedIndex(len(self.corpus))
+        premises = self.corpus.all_premises[index.lo:index.hi]
+        emb = torch.empty(len(premises), self.embedding_size, dtype=self.dtype, device=self.device)
+        if len(premises):
+            self.encode_texts(_Serialized(premises), batch_size=batch_size, out=emb)
+        index.set_embeddings(emb if emb.dtype == torch.bfloat16 else emb.to(torch.bfloat16))
+        self.sharded_index = index
+        return index
+
+    @torch.no_grad()
+    def retrieve_batch_sharded(self, states: Sequence[str], file_names: Sequence[str], theorem_full_names: Sequence[str],
+                               theorem_poses: Sequence[Any], k: int, group=None,
+                               **ops) -> Tuple[List[List[Premise]], List[List[float]]]:
+        """`retrieve_batch` over the row-sharded index (`ops`: injectable compute steps, see dist.sharded_topk)."""
+        index = self.reindex_corpus_sharded(group=group)
+        ctxs = [Context(f, t, Pos.from_any(p), s) for s, f, t, p in zip(states, file_names, theorem_full_names, theorem_poses)]
+        context_emb = self.encode_texts([c.serialize() for c in ctxs]).to(torch.bfloat16)
+        words = np.stack([self.corpus.accessible_mask_words_range(c.path, c.theorem_pos, index.lo, index.hi) for c in ctxs])
+        if words.shape[1] == 0:     # a rank without rows still takes part in the collective
+            words = np.zeros((len(ctxs), 1), dtype=np.uint32)
+        mask = torch.from_numpy(words.view(np.int32)).to(context_emb.device)
+        scores, idx, counts, _ = index.topk(context_emb, k, access_mask=mask, group=group, **ops)
+        if any(c < k for c in counts.cpu().tolist()):
+            raise ValueError
+        idx_h, scores_h = idx.cpu().tolist(), scores.cpu().tolist()
+        return [[self.corpus.all_premises[i] for i in row] for row in idx_h], scores_h
+
     # ------------------------------------------------------------------ index I/O (reference retrieval/index.py:37-40)
     def save_index(self, path: str) -> None:
         assert self.corpus is not None and not self.embeddings_staled

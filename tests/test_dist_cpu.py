@@ -125,3 +125,83 @@ def test_sharded_index_on_disk_roundtrip_and_resharding(tmp_path):
     assert ShardedIndex.load_corpus(directory) == {"stand-in": "corpus"}
     assert sorted(os.listdir(directory)) == ["corpus.pickle", "embeddings.00000-of-00002.pt", "embeddings.00001-of-00002.pt",
                                              "manifest.json"]
+
+
+def _toy_corpus():
+    from reprover_b200.corpus import Corpus, File, Pos, Premise
+    files = []
+    for f, (n, imports) in enumerate([(5, []), (4, ["T/F0.lean"]), (6, ["T/F1.lean"]), (3, [])]):
+        prem = [Premise(f"T/F{f}.lean", f"T.F{f}.l{j}", Pos(10 * j + 1, 0), Pos(10 * j + 5, 0), f"theorem l{j} : x{f}_{j} = y")
+                for j in range(n)]
+        files.append((File(f"T/F{f}.lean", prem), imports))
+    return Corpus.from_files(files)
+
+
+def _retr_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from reprover_b200.corpus import Pos
+        from tests.test_host_cpu import _stub_retriever
+        r = _stub_retriever(10**9)
+        r.load_corpus(_toy_corpus())
+        index = r.reindex_corpus_sharded()
+        assert r.reindex_corpus_sharded() is index and len(r.encoder.calls) == 1     # fresh: not re-encoded
+        states = ["⊢ a = b", "h : p\n⊢ q", "⊢ True"]
+        files, poses = ["T/F2.lean", "T/F1.lean", "T/F3.lean"], [Pos(25, 0), Pos(100, 0), Pos(100, 0)]
+        prem, scores = r.retrieve_batch_sharded(states, files, ["t"] * 3, poses, 3,
+                                                local_topk=_oracle_local_topk, merge=_oracle_merge)
+        try:
+            r.retrieve_batch_sharded(states[2:], files[2:], ["t"], poses[2:], 4,      # F3 alone has 3 premises
+                                     local_topk=_oracle_local_topk, merge=_oracle_merge)
+            raised = False
+        except ValueError:
+            raised = True
+        out_q.put((rank, (index.lo, index.hi), [[p.full_name for p in row] for row in prem], scores, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_retriever_sharded_mode_equals_the_unsharded_walk():
+    """`reindex_corpus_sharded` / `retrieve_batch_sharded` on two gloo ranks (stub encoder, oracle compute
+    steps): each rank encodes only its rows, slices the accessibility bitmask to its row range, and both
+    ranks return what the reference walk returns on the whole index — including the ValueError."""
+    from oracle import reference_path as ref
+    from reprover_b200.corpus import Context, Pos
+    from tests.test_host_cpu import _stub_retriever
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_retr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    corpus = _toy_corpus()
+    assert [r[1] for r in results] == [(0, 9), (9, 18)]
+    full = _stub_retriever(10**9)
+    E = full.encode_texts([p.serialize() for p in corpus.all_premises]).to(torch.bfloat16).float()
+    states = ["⊢ a = b", "h : p\n⊢ q", "⊢ True"]
+    Q = full.encode_texts(states).to(torch.bfloat16).float()
+    ctxs = [Context(f, "t", pos, s) for s, f, pos in zip(states, ["T/F2.lean", "T/F1.lean", "T/F3.lean"],
+                                                          [Pos(25, 0), Pos(100, 0), Pos(100, 0)])]
+    want_p, want_s = ref.get_nearest_premises(corpus, E, ctxs, Q, 3)
+    for _, _, names, scores, raised in results:
+        assert names == [[p.full_name for p in row] for row in want_p]
+        assert np.allclose(scores, want_s, atol=1e-6)
+        assert raised
+
+
+def test_accessible_mask_words_range_is_a_bit_slice():
+    from reprover_b200.corpus import Pos
+    c = _toy_corpus()
+    full = np.unpackbits(c.accessible_mask_words("T/F2.lean", Pos(25, 0)).view(np.uint8), bitorder="little")[: len(c)]
+    for lo, hi in [(0, 18), (0, 9), (9, 18), (3, 4), (7, 7), (1, 17)]:
+        w = c.accessible_mask_words_range("T/F2.lean", Pos(25, 0), lo, hi)
+        assert w.dtype == np.uint32 and len(w) == (hi - lo + 31) // 32
+        bits = np.unpackbits(w.view(np.uint8), bitorder="little") if len(w) else np.zeros(0, dtype=np.uint8)
+        assert bits[: hi - lo].tolist() == full[lo:hi].tolist() and not bits[hi - lo:].any()
