@@ -88,3 +88,23 @@ def test_batched_predictions_match_the_reference_retriever(gold_setup):
         decisive = len(got_names) if i < 2 else 2      # third place of the last context: 0.6957 vs 0.6928
         assert got_names[:decisive] == want["retrieved_premises"][:decisive], (i, got_names, want["retrieved_premises"])
         assert np.allclose(scores[i][:decisive], want_scores[:decisive], atol=SCORE_ATOL)
+
+
+def test_sharded_mode_on_one_rank_equals_the_unsharded_retriever(gold_setup):
+    """`reindex_corpus_sharded` / `retrieve_batch_sharded` with a world of one (no process group): the
+    row range is the whole corpus, the bitmask slice is the whole bitmask, the merge has one part — the
+    answer must be the unsharded one (the two-rank plumbing is tested with gloo in tests/test_dist_cpu.py
+    and with NCCL in tests/test_dist_gpu.py)."""
+    r, meta = gold_setup["retr"], gold_setup["meta"]
+    ctxs = meta["validation"]["contexts"]
+    args = ([c["state"] for c in ctxs], [c["path"] for c in ctxs], [c["theorem_full_name"] for c in ctxs],
+            [Pos(*c["pos"]) for c in ctxs], 3)
+    want_p, want_s = r.retrieve_batch(*args)
+    index = r.reindex_corpus_sharded()
+    assert (index.lo, index.hi) == (0, len(r.corpus)) and index.embeddings.dtype == torch.bfloat16
+    assert torch.equal(index.embeddings, r.corpus_embeddings.to(torch.bfloat16))
+    got_p, got_s = r.retrieve_batch_sharded(*args)
+    assert [[p.full_name for p in row] for row in got_p] == [[p.full_name for p in row] for row in want_p]
+    assert got_s == want_s
+    with pytest.raises(ValueError):
+        r.retrieve_batch_sharded(args[0][2:], args[1][2:], args[2][2:], [Pos(7, 0)], 2)
