@@ -75,6 +75,7 @@ class B200PremiseRetriever:
     def load_corpus(self, path_or_corpus: Union[str, Corpus]) -> None:
         """Attach a corpus: a `Corpus`, a `corpus.jsonl` path (stale index) or a pickled
         `IndexedCorpus` (fresh index)."""
+        self.sharded_index = None   # a row-sharded index belongs to the corpus it was built from
         if isinstance(path_or_corpus, Corpus):
             self.corpus = path_or_corpus
             self.corpus_embeddings = None
