@@ -97,8 +97,13 @@ def test_python_product_path_refuses_cpu():
 def test_product_path_never_imports_oracle():
     """No module under reprover_b200/ may import, link or shell out to anything under oracle/
     (_build.py only *compiles* the checker)."""
-    for path in (ROOT / "reprover_b200").rglob("*.py"):
+    for path in list((ROOT / "reprover_b200").rglob("*.py")) + list((ROOT / "tools").rglob("*.py")):
         text = path.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+    # outside tests/, only the two sanctioned call sites touch it: smoke() and bench.py's CPU legs
+    for name in ("bench.py", "__graft_entry__.py"):
+        text = (ROOT / name).read_text()
+        for m in re.finditer(r"^(\s*)(from|import)\s+oracle\b", text, flags=re.M):
+            assert len(m.group(1)) >= 4, f"{name}: oracle must only be imported inside the functions that use it as checker / stopwatch"
     for path in (ROOT / "reprover_b200" / "csrc").iterdir():
         assert not re.search(r'#include\s+[<"][^>"]*oracle', path.read_text()), path
