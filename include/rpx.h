@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RPX_VERSION 100 /* 0.1.0 */
+#define RPX_VERSION 200 /* 0.2.0 */
 
 enum {
   RPX_OK = 0,
@@ -156,16 +156,55 @@ int rpx_encoder_read_profile(rpx_encoder* enc, float* h_ms, int64_t* h_launches)
  * argsort tie order): score descending, then index ascending, where `score` is
  * the canonical fp64 dot product of the bf16 operands (oracle/rpx_oracle.c:
  * rpx_oracle_dot64).  out_scores are that value rounded to fp32.
- *   d_Q [nq, d] bf16, d_E [n, d] bf16 (the dtype the reference's GPU path holds
- *   the index in, retrieval/model.py:363-366); d % 64 == 0; 1 <= k <= 256.
+ *
+ * Exactness.  The fast paths rank by an fp32 score (tensor-core or FMA accumulation)
+ * and re-score a superset of the answer in fp64.  A per-query guard compares the k-th
+ * re-scored entry with the best fp32 score any row outside the re-scored set can have;
+ * when the gap is inside the accumulation error bound (c(d) * ||q|| * max_i ||e_i||)
+ * the query is recomputed by an exact fp64 pass over all admissible rows.  The result is
+ * therefore the contract's answer on any input (near-duplicate rows included); only the
+ * time depends on the data.
+ *
+ * rpx_index — a handle on a [n, d] bf16 matrix (what the reference keeps in
+ * `self.corpus_embeddings`, retrieval/model.py:190, 363-366; d % 64 == 0).  Creating it
+ * runs the one pass that depends only on the matrix (row-norm bound of the guard).  The
+ * caller owns the matrix and the `rpx_index_state_bytes()` bytes of device state it hands in;
+ * both must outlive the handle, and the handle must be re-created after the matrix changes.
+ * One call at a time per handle (the device state holds the call's counters).
+ */
+typedef struct rpx_index rpx_index; /* opaque */
+size_t rpx_index_state_bytes(void);
+int rpx_index_create(const void* d_E, int64_t n, int32_t d, void* d_state, void* stream, rpx_index** out);
+int rpx_index_destroy(rpx_index* ix);
+/* Diagnostics (synchronises `stream`): the row-norm bound, the largest |fp32 - fp64| score difference
+ * and the largest epsilon any guard has seen, and how many queries took the exact pass. */
+int rpx_index_stats(rpx_index* ix, void* stream, float* h_norm_max, float* h_max_err, float* h_max_eps,
+                    int64_t* h_n_exact);
+
+/* Path selection flags of rpx_index_topk (0 = automatic: streaming kernel for nq <= 4, tcgen05
+ * kernel otherwise, exact pass for k > 200).  The forcing flags exist for parity tests. */
+enum { RPX_TOPK_AUTO = 0, RPX_TOPK_FORCE_MMA = 1, RPX_TOPK_FORCE_STREAM = 2, RPX_TOPK_FORCE_EXACT = 4 };
+
+/*   d_Q [nq, d] bf16; 1 <= k <= 1024 (k <= 200 on the fast paths).
  *   d_access_mask  optional bitmask, row q = mask_stride_words uint32 words, bit
  *                  (i & 31) of word i >> 5 set <=> premise i is accessible to query q
  *                  (the `p in accessible_premises` test, common.py:313-318).
  *   d_out_count    optional [nq]: number of valid results (< k when fewer than k
  *                  candidates exist; the tail is idx = -1, score = -inf).
+ *   d_out_scores64 optional [nq, k] fp64 scores.
+ *   d_out_packed   optional [nq, k, 2] int64: (fp64 score bits, index) records — the
+ *                  payload of the multi-GPU all-gather (rpx_topk_merge_packed).
  *   idx_offset     added to every output index (row offset of this shard).
  */
-size_t rpx_sim_topk_workspace_bytes(int32_t nq, int32_t k);
+size_t rpx_index_topk_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k);
+int rpx_index_topk(rpx_index* ix, const void* d_Q, int32_t nq, int32_t k, const uint32_t* d_access_mask,
+                   int64_t mask_stride_words, float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx,
+                   int32_t* d_out_count, int64_t* d_out_packed, int64_t idx_offset, int32_t flags,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* One-shot form without a handle: same result, but the row-norm pass over E runs on every call
+ * (one extra read of the matrix).  Use rpx_index_* when the same matrix is queried repeatedly. */
+size_t rpx_sim_topk_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k);
 int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_t d, int32_t k,
                  const uint32_t* d_access_mask, int64_t mask_stride_words, float* d_out_scores,
                  double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count,
@@ -173,11 +212,15 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
 
 /* k-way merge of per-shard results after the all-gather:
  * inputs [n_parts, nq, k] (fp64 scores, int64 global indices; each [part, query] row sorted under
- * the ordering contract with its empty slots, idx < 0, at the end — exactly what rpx_sim_topk
- * emits), outputs the global top-k per query under the same ordering contract. */
+ * the ordering contract with its empty slots, idx < 0, at the end — exactly what the top-k calls
+ * emit), outputs the global top-k per query under the same ordering contract.
+ * The _packed form takes the gathered `d_out_packed` records, [n_parts, nq, k, 2] int64. */
 int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_parts, int32_t nq,
                    int32_t k, float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx,
                    int32_t* d_out_count, void* stream);
+int rpx_topk_merge_packed(const int64_t* d_packed, int32_t n_parts, int32_t nq, int32_t k,
+                          float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx,
+                          int32_t* d_out_count, void* stream);
 
 /* ------------------------------------------------------------------- test utilities
  * Plain tcgen05 GEMM used by the parity tests of the contraction core:

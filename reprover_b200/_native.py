@@ -20,6 +20,12 @@ RPX_ERR_UNSUPPORTED = 3
 RPX_ERR_WORKSPACE = 4
 RPX_ERR_MASK = 5
 
+RPX_TOPK_AUTO = 0
+RPX_TOPK_FORCE_MMA = 1
+RPX_TOPK_FORCE_STREAM = 2
+RPX_TOPK_FORCE_EXACT = 4
+TOPK_MAX_K = 1024
+
 RPX_DTYPE_BF16 = 0
 RPX_DTYPE_F32 = 1
 RPX_N_KERNEL_CLASSES = 7
@@ -84,12 +90,23 @@ _SIGNATURES = {
     "rpx_encoder_set_debug_hidden": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rpx_encoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "rpx_encoder_read_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
-    "rpx_sim_topk_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rpx_index_state_bytes": (C.c_size_t, []),
+    "rpx_index_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rpx_index_destroy": (C.c_int, [C.c_void_p]),
+    "rpx_index_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "rpx_index_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "rpx_index_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "rpx_sim_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "rpx_sim_topk": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rpx_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rpx_topk_merge_packed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "rpx_gemm_bf16_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p]),
     "rpx_gemm2_bf16_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -20,6 +20,7 @@
 
 #include "rpx_gemm_launch.cuh"
 #include "rpx_kernels.cuh"
+#include "rpx_topk_common.cuh"
 
 namespace rpx {
 
@@ -37,11 +38,7 @@ constexpr int kSampleTiles = RPX_SIM_SAMPLE_TILES;  // 32 x 256 = 8192 sampled p
 #define RPX_SIM_2CTA 1  // 0: stage 1 always on the 1-CTA kernel
 #endif
 constexpr int kSelSlack = RPX_SIM_SEL_SLACK;        // stage 2 re-scores between n_res and n_res + kSelSlack rows
-constexpr unsigned kFull = 0xffffffffu;
-
-// Monotone map float bits -> uint32 (a > b  <=>  fkey(a) > fkey(b), -0 < +0).
-__device__ __forceinline__ uint32_t fkey(uint32_t u) { return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
-__device__ __forceinline__ uint32_t unkey(uint32_t k) { return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k; }
+constexpr unsigned kFull = kFullMask;
 
 // EPL = candidate entries per lane: a list holds CAP = 32*EPL entries and is compacted back to
 // about KEEP (<= CAP/2) when it fills.  KEEP is the size of the candidate superset a CTA
@@ -50,6 +47,7 @@ __device__ __forceinline__ uint32_t unkey(uint32_t k) { return (k & 0x80000000u)
 struct SimTopkParams {
   uint2* cand;           // [grid][128][CAP]  (score bits, local index)
   int32_t* cnt;          // [grid][128]
+  float* thr_out;        // [grid][128] final pass threshold of each list: nothing above it was ever dropped
   uint32_t* gthr;        // [tiles_m*128] shared per-query threshold (monotone key, atomicMax)
   uint32_t* gmin;        // [tiles_m*128] min over CTAs of their first published rank_r-th best key
   uint32_t* gcnt;        // [tiles_m*128] number of CTAs that have published into gmin
@@ -300,6 +298,7 @@ struct EpiSimTopk {
     // stage 2 keeps all lists of a query in shared memory: shorten them only if they would not fit
     if (p.final_max < CAP && __any_sync(kFull, count() > p.final_max)) compact_warp(p.final_max);
     p.cnt[slot] = count();
+    p.thr_out[slot] = thr;
   }
 };
 
@@ -357,22 +356,6 @@ struct EpiSampleScores {
   __device__ void finish() {}
 };
 
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity);
-
-// Block-wide sum of per-thread counts with ONE barrier per call: warp REDUX, one shared-memory
-// atomic per warp, three rotating counters (slot i % 3 is used by call i and cleared during call
-// i + 1, well before call i + 3 adds to it again).  `slots` must be zero on the first call.
-__device__ __forceinline__ int block_count(int m, int* slots, int iter) {
-  m = __reduce_add_sync(kFull, m);
-  int* cur = slots + iter % 3;
-  if ((threadIdx.x & 31) == 0 && m != 0) atomicAdd(cur, m);
-  __syncthreads();
-  const int total = *cur;
-  if (threadIdx.x == 0) slots[(iter + 2) % 3] = 0;
-  return total;
-}
-
 // One CTA per query: gthr[q] = (n_res-th largest sample key) - 1, or 0 when fewer than n_res
 // sampled premises are admissible.
 __global__ void __launch_bounds__(256)
@@ -424,64 +407,6 @@ sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_r
 
 // ------------------------------------------------------------------------------------ stage 2
 
-// Canonical fp64 dot product (identical in oracle/rpx_oracle.c::rpx_oracle_dot64):
-// lane l accumulates, in increasing j then e order, the elements d = (j*32 + l)*8 + e
-// (e = 0..7) with acc = acc + a*b — the bf16 x bf16 product is exact (even in fp32), so this is
-// one rounding per addition — and the 32 partials are combined by the xor butterfly
-// 16, 8, 4, 2, 1 (p = p + p_partner).
-__device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restrict__ qrow,  // smem or global
-                                                  const __nv_bfloat16* __restrict__ erow, int d, int lane) {
-  double acc = 0.0;
-  const int chunks = d >> 3;
-  // all of this lane's 16-byte loads of the (cold, DRAM-resident) index row go out before the first
-  // dependent fma; the summation order is unchanged
-  constexpr int kMaxIter = 8;  // d <= 8 * 32 * 8 = 2048 takes the batched path
-  if (chunks <= kMaxIter * 32) {
-    uint4 ev[kMaxIter];
-#pragma unroll
-    for (int it = 0; it < kMaxIter; ++it) {
-      const int ch = lane + it * 32;
-      ev[it] = ch < chunks ? *reinterpret_cast<const uint4*>(erow + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int it = 0; it < kMaxIter; ++it) {
-      const int ch = lane + it * 32;
-      if (ch < chunks) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
-        const uint32_t ew[4] = {ev[it].x, ev[it].y, ev[it].z, ev[it].w};
-        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          // bf16 x bf16 is exact in fp32 (8 + 8 significand bits), so the fp32 product converted to
-          // fp64 equals the exact product: one F2F per element instead of two (the fp32->fp64
-          // conversion pipe, not HBM, was the limiter of this kernel)
-          const float p0 = __uint_as_float(qw[w] << 16) * __uint_as_float(ew[w] << 16);
-          const float p1 = __uint_as_float(qw[w] & 0xFFFF0000u) * __uint_as_float(ew[w] & 0xFFFF0000u);
-          acc += (double)p0;
-          acc += (double)p1;
-        }
-      }
-    }
-  } else {
-    for (int ch = lane; ch < chunks; ch += 32) {
-      const uint4 ev = *reinterpret_cast<const uint4*>(erow + ch * 8);
-      const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ch * 8);
-      const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
-      const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const float p0 = __uint_as_float(qw[w] << 16) * __uint_as_float(ew[w] << 16);
-        const float p1 = __uint_as_float(qw[w] & 0xFFFF0000u) * __uint_as_float(ew[w] & 0xFFFF0000u);
-        acc += (double)p0;
-        acc += (double)p1;
-      }
-    }
-  }
-#pragma unroll
-  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
-  return acc;
-}
-
 // Threads per query in stage 2: 512 when few queries are in flight (one query's latency is what
 // matters: Q = 1 0.192 vs 0.202 ms, Q = 64 0.166 vs 0.178 ms), 256 when there are enough queries to
 // fill the GPU (4 CTAs per SM instead of 2 overlap the staging / bisection / gather phases of different
@@ -489,49 +414,47 @@ __device__ __forceinline__ double dot64_canonical(const __nv_bfloat16* __restric
 constexpr int kSelThreadsLatency = 512, kSelThreadsThroughput = 256, kSelThroughputMinQueries = 512;
 constexpr int kSelMax = 288;  // >= largest re-score set (k + margin + selection slack)
 
-__device__ __forceinline__ uint64_t ckey(uint2 e) {
-  // composite: score (monotone) high, ~index low => larger key == better under (score desc, index asc)
-  return ((uint64_t)fkey(e.x) << 32) | (uint64_t)(0xFFFFFFFFu - e.y);
-}
-
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, T* red, Op op, T identity) {
-  for (int off = 16; off; off >>= 1) v = op(v, __shfl_xor_sync(kFull, v, off));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  T r = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : identity;
-  if (threadIdx.x < 32) {
-    for (int off = 16; off; off >>= 1) r = op(r, __shfl_xor_sync(kFull, r, off));
-    if (threadIdx.x == 0) red[0] = r;
-  }
-  __syncthreads();
-  r = red[0];
-  __syncthreads();
-  return r;
-}
+__device__ __forceinline__ uint64_t ckey(uint2 e) { return ckey32(e.x, e.y); }
 
 // One CTA per query.  The query's candidate lists (one per stage-1 CTA that served its block,
 // each <= list_max entries) are staged in shared memory as 64-bit composite keys; a bisection
-// picks the `n_res` best (+ <= 16), which are re-scored in fp64 and ranked exactly.
+// picks the `n_res` best (+ <= 16), which are re-scored in fp64 and ranked exactly.  The exactness
+// guard (rpx_topk_common.cuh) then compares the k-th re-scored entry with the best fp32 score any
+// row outside the re-scored set can have — the largest final threshold of the query's lists
+// (`thr_out`: everything stage 1 dropped scored at or below it) or the selection threshold — and
+// flags the query for the exact path when the gap is inside the tensor-core error bound.
+struct SelectOut {
+  float* scores;
+  double* scores64;
+  int64_t* idx;
+  int32_t* count;
+  int64_t* packed;
+  int64_t idx_offset;
+  GuardOut guard;
+  float guard_coeff;
+  int q_base;  // number of query 0 of this launch within the call
+};
+
 template <int kSelThreads>
 __global__ void __launch_bounds__(kSelThreads)
-select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int list_max,
-                      int n_res, int grid_sim, int tiles_m, const __nv_bfloat16* __restrict__ Q,
-                      const __nv_bfloat16* __restrict__ E, int d, int k, int64_t idx_offset,
-                      float* __restrict__ out_scores, double* __restrict__ out_scores64,
-                      int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cnt, const float* __restrict__ thr_out,
+                      int cap, int list_max, int n_res, int grid_sim, int tiles_m, const __nv_bfloat16* __restrict__ Q,
+                      const __nv_bfloat16* __restrict__ E, int d, int k, const SelectOut o) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int n_seg = grid_sim / tiles_m;
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_raw);                                  // [d]
   double* sel_score = reinterpret_cast<double*>(sm_raw + (((size_t)d * 2 + 15) & ~(size_t)15));   // [kSelMax]
   uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_score + kSelMax);                            // [kSelMax]
-  int* seg_off = reinterpret_cast<int*>(sel_idx + kSelMax);                                        // [n_seg + 1]
+  float* sel_s32 = reinterpret_cast<float*>(sel_idx + kSelMax);                                    // [kSelMax]
+  int* seg_off = reinterpret_cast<int*>(sel_s32 + kSelMax);                                        // [n_seg + 1]
   uint64_t* keys = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(seg_off + n_seg + 1) + 15) & ~(uintptr_t)15);                   // [n_seg * list_max]
   __shared__ uint64_t red64[32];
+  __shared__ float redf[32];
   __shared__ int cslots[3];
   __shared__ int n_sel;
+  __shared__ double kth_score;
+  __shared__ uint32_t kth_idx;
 
   const int q = blockIdx.x;
   const int q_blk = q / kBlockM, row = q % kBlockM;
@@ -540,13 +463,22 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
   for (int i = tid; i < d / 8; i += kSelThreads)
     reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(Q + (size_t)q * d)[i];
   if (tid < 3) cslots[tid] = 0;
+  if (tid == 0) n_sel = 0;
+  // list lengths and final thresholds of the query's segments (independent loads, one per thread)
+  float tdrop = -INFINITY;
+  for (int s = tid; s < n_seg; s += kSelThreads) {
+    const int slot = (q_blk + s * tiles_m) * kBlockM + row;
+    const int c = cnt[slot];
+    seg_off[s + 1] = c < list_max ? c : list_max;  // (stage 1 guarantees c <= list_max)
+    tdrop = fmaxf(tdrop, thr_out[slot]);
+  }
+  tdrop = block_reduce<float>(tdrop, redf, [](float a, float b) { return fmaxf(a, b); }, -INFINITY);
   if (tid == 0) {
-    n_sel = 0;
     int acc = 0;
     for (int s = 0; s < n_seg; ++s) {
+      const int c = seg_off[s + 1];
       seg_off[s] = acc;
-      int c = cnt[(q_blk + s * tiles_m) * kBlockM + row];
-      acc += c < list_max ? c : list_max;  // (stage 1 guarantees c <= list_max)
+      acc += c;
     }
     seg_off[n_seg] = acc;
   }
@@ -557,11 +489,11 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
   uint64_t kmin = ~0ull, kmax = 0ull;
   for (int s = warp; s < n_seg; s += kSelThreads / 32) {
     const int slot = (q_blk + s * tiles_m) * kBlockM + row;
-    const int o = seg_off[s], c = seg_off[s + 1] - o;
+    const int o0 = seg_off[s], c = seg_off[s + 1] - o0;
     const uint2* b = cand + (size_t)slot * cap;
     for (int i = lane; i < c; i += 32) {
       const uint64_t key = ckey(b[i]);
-      keys[o + i] = key;
+      keys[o0 + i] = key;
       kmin = key < kmin ? key : kmin;
       kmax = key > kmax ? key : kmax;
     }
@@ -593,18 +525,30 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
     const uint64_t key = keys[i];
     if (key >= lo) {
       const int pos = atomicAdd(&n_sel, 1);
-      if (pos < kSelMax) sel_idx[pos] = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+      if (pos < kSelMax) {
+        sel_idx[pos] = ckey_idx(key);
+        sel_s32[pos] = ckey_score(key);
+      }
     }
   }
   __syncthreads();
   const int ns = n_sel < kSelMax ? n_sel : kSelMax;
 
   // ---- exact fp64 re-scoring, one warp per candidate
+  float err = 0.f, q2 = 0.f;
   for (int c = warp; c < ns; c += kSelThreads / 32) {
     const double s = dot64_canonical(sq, E + (size_t)sel_idx[c] * d, d, lane);
-    if (lane == 0) sel_score[c] = s;
+    if (lane == 0) {
+      sel_score[c] = s;
+      err = fmaxf(err, fabsf((float)(s - (double)sel_s32[c])));
+    }
   }
-  __syncthreads();
+  for (int i = tid; i < d; i += kSelThreads) {
+    const float v = __bfloat162float(sq[i]);
+    q2 = fmaf(v, v, q2);
+  }
+  err = block_reduce<float>(err, redf, [](float a, float b) { return fmaxf(a, b); }, 0.f);
+  q2 = block_reduce<float>(q2, redf, [](float a, float b) { return a + b; }, 0.f);
 
   // ---- rank by counting under (score desc, index asc); ranks are a permutation
   for (int c = tid; c < ns; c += kSelThreads) {
@@ -616,23 +560,44 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
       rank += (sj > sc || (sj == sc && sel_idx[j] < ic)) ? 1 : 0;
     }
     if (rank < k) {
-      const size_t o = (size_t)q * k + rank;
-      out_scores[o] = (float)sc;
-      if (out_scores64) out_scores64[o] = sc;
-      out_idx[o] = (int64_t)ic + idx_offset;
+      const size_t oo = (size_t)q * k + rank;
+      o.scores[oo] = (float)sc;
+      if (o.scores64) o.scores64[oo] = sc;
+      o.idx[oo] = (int64_t)ic + o.idx_offset;
+      if (o.packed) {
+        o.packed[2 * oo] = __double_as_longlong(sc);
+        o.packed[2 * oo + 1] = (int64_t)ic + o.idx_offset;
+      }
+    }
+    if (rank == k - 1) {
+      kth_score = sc;
+      kth_idx = ic;
     }
   }
   const int valid = ns < k ? ns : k;
   for (int r = valid + tid; r < k; r += kSelThreads) {
-    const size_t o = (size_t)q * k + r;
-    out_scores[o] = -INFINITY;
-    if (out_scores64) out_scores64[o] = -INFINITY;
-    out_idx[o] = -1;
+    const size_t oo = (size_t)q * k + r;
+    o.scores[oo] = -INFINITY;
+    if (o.scores64) o.scores64[oo] = -INFINITY;
+    o.idx[oo] = -1;
+    if (o.packed) {
+      o.packed[2 * oo] = __double_as_longlong(-INFINITY);
+      o.packed[2 * oo + 1] = -1;
+    }
   }
-  if (out_count && tid == 0) out_count[q] = valid;
+  __syncthreads();
+  if (tid == 0) {
+    if (o.count) o.count[q] = valid;
+    float u = tdrop;                                      // dropped by a stage-1 threshold / compaction
+    if (total > ns) u = fmaxf(u, ckey_score(lo));          // staged but not selected for re-scoring
+    guard_decide(o.guard, o.q_base + q, k, ns, kth_score, kth_idx, u, q2, o.guard_coeff, err);
+  }
 }
 
 // ------------------------------------------------------------------------------------ stage 3
+// PACKED: the parts arrive as one [n_parts, nq, k, 2] int64 buffer of (fp64 score bits, index) records —
+// exactly what the all-gather of every rank's `out_packed` delivers — instead of two planes.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__ idx, int n_parts, int nq, int k,
                   float* __restrict__ out_scores, double* __restrict__ out_scores64, int64_t* __restrict__ out_idx,
@@ -649,8 +614,14 @@ topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__
   for (int i = tid; i < n; i += blockDim.x) {
     const int part = i / k, r = i % k;
     const size_t src = ((size_t)part * nq + q) * k + r;
-    s[i] = scores[src];
-    ix[i] = idx[src];
+    if (PACKED) {
+      const longlong2 rec = reinterpret_cast<const longlong2*>(idx)[src];
+      s[i] = __longlong_as_double(rec.x);
+      ix[i] = rec.y;
+    } else {
+      s[i] = scores[src];
+      ix[i] = idx[src];
+    }
     local_valid += ix[i] >= 0 ? 1 : 0;
   }
   atomicAdd(&n_valid, local_valid);
@@ -706,16 +677,16 @@ struct SimPlan {
 constexpr size_t kSelSmemBudget = 200 * 1024;
 
 size_t sel_smem_bytes(int d, int n_seg, int list_max) {
-  return (((size_t)d * 2 + 15) & ~(size_t)15) + kSelMax * (sizeof(double) + sizeof(uint32_t)) +
+  return (((size_t)d * 2 + 15) & ~(size_t)15) + kSelMax * (sizeof(double) + sizeof(uint32_t) + sizeof(float)) +
          ((size_t)n_seg + 1) * sizeof(int) + 16 + (size_t)n_seg * list_max * sizeof(uint64_t);
 }
 
 int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
-  RPX_REQUIRE(k >= 1 && k <= 200, RPX_ERR_UNSUPPORTED, "sim_topk: k=%d outside [1, 200]", k);
+  RPX_REQUIRE(k >= 1 && k <= kFastPathMaxK, RPX_ERR_UNSUPPORTED, "sim_topk: k=%d outside [1, %d]", k, kFastPathMaxK);
   RPX_REQUIRE(nq >= 1, RPX_ERR_INVALID, "sim_topk: nq=%d", nq);
-  // per-CTA candidate superset KEEP >= re-score set n_res = k + margin; the margin absorbs
-  // fp32 (tensor-core) vs fp64 rank flips at the k-th place
-  pl->n_res = k + (k / 8 > 12 ? k / 8 : 12);
+  // per-CTA candidate superset KEEP >= re-score set n_res = k + margin; the margin absorbs most
+  // fp32 (tensor-core) vs fp64 rank flips at the k-th place, the guard in stage 2 catches the rest
+  pl->n_res = topk_n_res(k);
   pl->keep = k <= 100 ? 128 : 256;
   pl->epl = 16;
   pl->cap = 32 * pl->epl;
@@ -736,7 +707,7 @@ int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
   pl->grid = n_seg * pl->tiles_m;
   pl->sel_smem = sel_smem_bytes(d, n_seg, pl->list_max);
   pl->cand_bytes = align_up((size_t)pl->grid * kBlockM * pl->cap * sizeof(uint2), 256);
-  pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);
+  pl->cnt_bytes = align_up((size_t)pl->grid * kBlockM * sizeof(int32_t), 256);  // also the size of thr_out
   pl->gthr_bytes = align_up((size_t)pl->tiles_m * kBlockM * sizeof(uint32_t), 256);
   // sampling pass: up to kSampleTiles tiles of 256 premises, score matrix capped at 64 MB
   pl->sample_tiles = kSampleTiles;
@@ -744,7 +715,7 @@ int plan_sim(int nq, int k, int d, int num_sms, SimPlan* pl) {
          (size_t)pl->tiles_m * kBlockM * pl->sample_tiles * kSimBlockN * sizeof(float) > (size_t)64 << 20)
     pl->sample_tiles /= 2;
   pl->sample_bytes = align_up((size_t)pl->tiles_m * kBlockM * pl->sample_tiles * kSimBlockN * sizeof(float), 256);
-  pl->total = pl->cand_bytes + pl->cnt_bytes + 3 * pl->gthr_bytes + pl->sample_bytes;  // + gthr, gmin, gcnt
+  pl->total = pl->cand_bytes + 2 * pl->cnt_bytes + 3 * pl->gthr_bytes + pl->sample_bytes;  // + thr_out; gthr, gmin, gcnt
   return RPX_OK;
 }
 
@@ -806,46 +777,39 @@ int launch_sim_epi_paired(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E
 }
 
 }  // namespace
-}  // namespace rpx
 
-using namespace rpx;
-
-extern "C" {
-
-size_t rpx_sim_topk_workspace_bytes(int32_t nq, int32_t k) {
+size_t mma_topk_workspace_bytes(int nq, int k, int d, int num_sms) {
   SimPlan pl;
-  // sized for the largest Blackwell SM count so the query works without a device (d only
-  // shrinks the plan, so the smallest legal d gives the upper bound)
-  if (plan_sim(nq, k, 64, 160, &pl) != RPX_OK) return 0;
+  if (plan_sim(nq, k, d, num_sms, &pl) != RPX_OK) return 0;
   return pl.total + 256;
 }
 
-int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_t d, int32_t k,
-                 const uint32_t* d_access_mask, int64_t mask_stride_words, float* d_out_scores,
-                 double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count, int64_t idx_offset,
-                 void* d_workspace, size_t workspace_bytes, void* stream) {
-  RPX_REQUIRE(d_Q && d_out_scores && d_out_idx && d_workspace, RPX_ERR_INVALID, "rpx_sim_topk: null argument");
-  RPX_REQUIRE(d_E != nullptr || n == 0, RPX_ERR_INVALID, "rpx_sim_topk: null index");
-  RPX_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX - 512, RPX_ERR_UNSUPPORTED, "rpx_sim_topk: n=%lld out of range", (long long)n);
-  RPX_REQUIRE(d > 0 && d % 64 == 0 && d <= 8192, RPX_ERR_UNSUPPORTED, "rpx_sim_topk: d=%d must be a multiple of 64 (<= 8192)", d);
-  RPX_REQUIRE(d_access_mask == nullptr || mask_stride_words * 32 >= n, RPX_ERR_INVALID, "rpx_sim_topk: mask stride too small");
+// The tcgen05 path: [stage 0 sampling pass + threshold] -> stage 1 (fused MMA + top-k epilogue) ->
+// stage 2 (select, fp64 re-score, rank, guard).  `ws` is this path's private workspace.
+int run_mma_topk(const TopkCall& c, void* ws, size_t ws_bytes) {
+  const int nq = c.nq, d = c.d, k = c.k;
+  const int64_t n = c.n;
+  RPX_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX - 512, RPX_ERR_UNSUPPORTED, "sim_topk: n=%lld out of range", (long long)n);
+  RPX_REQUIRE(d > 0 && d % 64 == 0 && d <= 8192, RPX_ERR_UNSUPPORTED, "sim_topk: d=%d must be a multiple of 64 (<= 8192)", d);
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   SimPlan pl;
   RPX_TRY(plan_sim(nq, k, d, dev.num_sms, &pl));
-  RPX_REQUIRE(pl.total <= workspace_bytes, RPX_ERR_WORKSPACE, "rpx_sim_topk: workspace %zu < %zu", workspace_bytes, pl.total);
-  RPX_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, RPX_ERR_INVALID, "workspace must be 256-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint2* cand = reinterpret_cast<uint2*>(d_workspace);
-  int32_t* cnt = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes);
-  uint32_t* gthr = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_workspace) + pl.cand_bytes + pl.cnt_bytes);
+  RPX_REQUIRE(pl.total <= ws_bytes, RPX_ERR_WORKSPACE, "sim_topk: workspace %zu < %zu", ws_bytes, pl.total);
+  RPX_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RPX_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t st = c.st;
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  uint2* cand = reinterpret_cast<uint2*>(base);
+  float* thr_out = reinterpret_cast<float*>(base + pl.cand_bytes);
+  int32_t* cnt = reinterpret_cast<int32_t*>(base + pl.cand_bytes + pl.cnt_bytes);
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(base + pl.cand_bytes + 2 * pl.cnt_bytes);
   uint32_t* gcnt = gthr + pl.gthr_bytes / 4;
   uint32_t* gmin = gcnt + pl.gthr_bytes / 4;
   float* sample = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(gmin) + pl.gthr_bytes);
   const int n_seg = pl.grid / pl.tiles_m;
   const int rank_r = ceil_div(pl.keep, n_seg);
-  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(d_Q);
-  const __nv_bfloat16* E = static_cast<const __nv_bfloat16*>(d_E);
+  const __nv_bfloat16* Q = c.Q;
+  const __nv_bfloat16* E = c.E;
   static thread_local int sel_configured = -1;
   if (sel_configured != dev.device) {
     RPX_CUDA_OK(cudaFuncSetAttribute(select_rescore_kernel<kSelThreadsLatency>,
@@ -861,19 +825,22 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
     //  because we keep tiles_m fixed and let the surplus query blocks be empty)
     RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + 2 * pl.gthr_bytes, st));  // cnt, gthr, gcnt are adjacent
     RPX_CUDA_OK(cudaMemsetAsync(gmin, 0xFF, pl.gthr_bytes, st));
-    const uint32_t* mask_c = d_access_mask ? d_access_mask + (size_t)q0 * mask_stride_words : nullptr;
+    // lists no stage-1 CTA visits keep count 0 and must not contribute a threshold: 0xFF bytes are a NaN,
+    // which the fmaxf() reduction in stage 2 skips
+    RPX_CUDA_OK(cudaMemsetAsync(thr_out, 0xFF, pl.cnt_bytes, st));
+    const uint32_t* mask_c = c.mask ? c.mask + (size_t)q0 * c.mask_stride : nullptr;
     const int64_t tiles_n_all = ceil_div64(n, kSimBlockN);
     if (tiles_n_all >= 4 * (int64_t)pl.sample_tiles) {
       // stage 0: starting thresholds from a strided sample of the corpus (overwrites gthr)
       const int ld = pl.sample_tiles * kSimBlockN;
-      EpiSampleScores::Params sp{sample, ld, mask_c, mask_stride_words, nq_c, (int)n};
+      EpiSampleScores::Params sp{sample, ld, mask_c, c.mask_stride, nq_c, (int)n};
       RPX_TRY((launch_sim_epi<EpiSampleScores>(Q + (size_t)q0 * d, nq_c, E, n, d, sp, pl, st, pl.sample_tiles,
                                                 (int)(tiles_n_all / pl.sample_tiles))));
       sample_threshold_kernel<<<nq_c, 256, (size_t)ld * sizeof(uint32_t), st>>>(sample, ld, ld, pl.n_res, gthr);
       RPX_CUDA_OK(cudaGetLastError());
     }
     if (n > 0) {
-      SimTopkParams ep{cand, cnt, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, mask_stride_words, nq_c, (int)n, pl.tiles_m};
+      SimTopkParams ep{cand, cnt, thr_out, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, c.mask_stride, nq_c, (int)n, pl.tiles_m};
       if (pl.paired) {
         if (pl.keep == 128) {
           RPX_TRY((launch_sim_epi_paired<EpiSimTopk<16, 128, true>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
@@ -886,26 +853,33 @@ int rpx_sim_topk(const void* d_Q, int32_t nq, const void* d_E, int64_t n, int32_
         RPX_TRY((launch_sim_epi<EpiSimTopk<16, 256>>(Q + (size_t)q0 * d, nq_c, E, n, d, ep, pl, st)));
       }
     }
+    SelectOut so;
+    so.scores = c.out_scores + (size_t)q0 * k;
+    so.scores64 = c.out_scores64 ? c.out_scores64 + (size_t)q0 * k : nullptr;
+    so.idx = c.out_idx + (size_t)q0 * k;
+    so.count = c.out_count ? c.out_count + q0 : nullptr;
+    so.packed = c.out_packed ? c.out_packed + (size_t)q0 * k * 2 : nullptr;
+    so.idx_offset = c.idx_offset;
+    so.guard.state = c.state;
+    so.guard.flagged = c.flagged;
+    so.guard.bounds = c.bounds;
+    so.guard_coeff = guard_coeff_mma(d);
+    so.q_base = q0;
     if (nq_c >= kSelThroughputMinQueries) {
       select_rescore_kernel<kSelThreadsThroughput><<<nq_c, kSelThreadsThroughput, pl.sel_smem, st>>>(
-          cand, cnt, pl.cap, pl.list_max, pl.n_res, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, idx_offset,
-          d_out_scores + (size_t)q0 * k, d_out_scores64 ? d_out_scores64 + (size_t)q0 * k : nullptr,
-          d_out_idx + (size_t)q0 * k, d_out_count ? d_out_count + q0 : nullptr);
+          cand, cnt, thr_out, pl.cap, pl.list_max, pl.n_res, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, so);
     } else {
       select_rescore_kernel<kSelThreadsLatency><<<nq_c, kSelThreadsLatency, pl.sel_smem, st>>>(
-          cand, cnt, pl.cap, pl.list_max, pl.n_res, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, idx_offset,
-          d_out_scores + (size_t)q0 * k, d_out_scores64 ? d_out_scores64 + (size_t)q0 * k : nullptr,
-          d_out_idx + (size_t)q0 * k, d_out_count ? d_out_count + q0 : nullptr);
+          cand, cnt, thr_out, pl.cap, pl.list_max, pl.n_res, pl.grid, pl.tiles_m, Q + (size_t)q0 * d, E, d, k, so);
     }
     RPX_CUDA_OK(cudaGetLastError());
   }
   return RPX_OK;
 }
 
-int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_parts, int32_t nq, int32_t k,
-                   float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count,
-                   void* stream) {
-  RPX_REQUIRE(d_scores64 && d_idx && d_out_scores && d_out_idx, RPX_ERR_INVALID, "rpx_topk_merge: null argument");
+int launch_topk_merge(const double* d_scores64, const int64_t* d_idx_or_packed, bool packed, int n_parts, int nq, int k,
+                      float* d_out_scores, double* d_out_scores64, int64_t* d_out_idx, int32_t* d_out_count,
+                      cudaStream_t st) {
   RPX_REQUIRE(n_parts >= 1 && nq >= 1 && k >= 1, RPX_ERR_INVALID, "rpx_topk_merge: bad sizes");
   const size_t smem = (size_t)n_parts * k * 16;
   RPX_REQUIRE(smem <= 96 * 1024, RPX_ERR_UNSUPPORTED, "rpx_topk_merge: n_parts*k=%d too large", n_parts * k);
@@ -913,13 +887,18 @@ int rpx_topk_merge(const double* d_scores64, const int64_t* d_idx, int32_t n_par
   RPX_TRY(get_device_info(&dev));
   static thread_local int configured = -1;
   if (configured != dev.device) {
-    RPX_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    RPX_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    RPX_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = dev.device;
   }
-  topk_merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(d_scores64, d_idx, n_parts, nq, k, d_out_scores,
-                                                                       d_out_scores64, d_out_idx, d_out_count);
+  if (packed)
+    topk_merge_kernel<true><<<nq, 256, smem, st>>>(nullptr, d_idx_or_packed, n_parts, nq, k, d_out_scores, d_out_scores64,
+                                                   d_out_idx, d_out_count);
+  else
+    topk_merge_kernel<false><<<nq, 256, smem, st>>>(d_scores64, d_idx_or_packed, n_parts, nq, k, d_out_scores,
+                                                    d_out_scores64, d_out_idx, d_out_count);
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }
 
-}  // extern "C"
+}  // namespace rpx

@@ -32,44 +32,40 @@ def shard_bounds(n_rows: int, world_size: int) -> List[int]:
 
 
 def _default_local_topk(queries, shard, k, idx_offset, access_mask):
+    """This rank's [Q, k, 2] (fp64 score bits, global index) records, written by the top-k kernel itself."""
     from .retrieval_ops import sim_topk
 
-    s32, idx, cnt, s64 = sim_topk(queries, shard, k, access_mask=access_mask, idx_offset=idx_offset,
-                                  want_scores64=True)
-    return s64, idx
+    return sim_topk(queries, shard, k, access_mask=access_mask, idx_offset=idx_offset, want_packed=True)[-1]
 
 
-def _default_merge(scores64, idx):
-    from .retrieval_ops import topk_merge
+def _default_merge(gathered):
+    """[world, Q, k, 2] gathered records -> (scores fp32, idx, counts, scores fp64)."""
+    from .retrieval_ops import topk_merge_packed
 
-    s32, mi, mc, ms64 = topk_merge(scores64, idx)
-    return s32, mi, mc, ms64
+    return topk_merge_packed(gathered)
 
 
-def sharded_topk(queries: torch.Tensor, local_shard: torch.Tensor, k: int, row_offset: int,
+def sharded_topk(queries: torch.Tensor, local_shard, k: int, row_offset: int,
                  access_mask: Optional[torch.Tensor] = None, group=None,
                  local_topk: Callable = _default_local_topk, merge: Callable = _default_merge):
     """Global top-k over an index whose rows are spread over the ranks of `group`.
 
     `queries` [Q, D] must be identical on every rank (replicated); `local_shard` is this rank's
-    rows, `row_offset` its first global row.  `access_mask`, if given, is this rank's slice of the
-    per-query bitmask (bit i of the slice <=> global row row_offset + i).  Every rank returns the
-    same (scores fp32 [Q,k], global indices int64 [Q,k], counts int32 [Q], scores fp64 [Q,k]).
+    rows (tensor or `IndexHandle`), `row_offset` its first global row.  `access_mask`, if given, is this
+    rank's slice of the per-query bitmask (bit i of the slice <=> global row row_offset + i).  Every
+    rank returns the same (scores fp32 [Q,k], global indices int64 [Q,k], counts int32 [Q], scores fp64 [Q,k]).
+
+    Data path: the local kernel writes (fp64 score bits, int64 index) records [Q, k, 2]; ONE
+    `all_gather_into_tensor` concatenates the ranks' buffers; the merge kernel reads the gathered
+    [world, Q, k, 2] buffer as it is.  No staging copies on either side of the collective.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    s64, idx = local_topk(queries, local_shard, k, row_offset, access_mask)
+    packed = local_topk(queries, local_shard, k, row_offset, access_mask)
     if world == 1:
-        return merge(s64.unsqueeze(0), idx.unsqueeze(0))
-    # one all-gather: pack (fp64 score bits, int64 index) into a single [Q, k, 2] int64 buffer
-    packed = torch.stack([s64.view(torch.int64), idx], dim=-1).contiguous()
-    # (concatenated-along-dim-0 output: the layout both NCCL and gloo accept)
-    gathered = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=torch.int64,
-                           device=packed.device)
-    dist.all_gather_into_tensor(gathered, packed, group=group)
-    gathered = gathered.view((world,) + tuple(packed.shape))
-    all_s64 = gathered[..., 0].contiguous().view(torch.float64)
-    all_idx = gathered[..., 1].contiguous()
-    return merge(all_s64, all_idx)
+        return merge(packed.unsqueeze(0))
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=packed.device)
+    dist.all_gather_into_tensor(gathered.view(world * packed.shape[0], *packed.shape[1:]), packed, group=group)
+    return merge(gathered)
 
 
 class ShardedIndex:

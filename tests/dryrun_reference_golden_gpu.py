@@ -40,8 +40,9 @@ retrieval_ops.nearest_premises_device = oracle_nearest
 def loc(queries, shard, k, off, mask):
     words = None if mask is None else mask.numpy().view(np.uint32)
     s, i, _ = c_oracle.sim_topk(c_oracle.bf16_bits(queries), c_oracle.bf16_bits(shard), k, words, off)
-    return torch.from_numpy(s), torch.from_numpy(i)
-def mer(s64, idx):
+    return torch.stack([torch.from_numpy(s).view(torch.int64), torch.from_numpy(i)], dim=-1).contiguous()
+def mer(gathered):
+    s64, idx = gathered[..., 0].contiguous().view(torch.float64), gathered[..., 1].contiguous()
     s, i, c = c_oracle.topk_merge(s64.numpy(), idx.numpy())
     return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i), torch.from_numpy(c), torch.from_numpy(s)
 rdist.sharded_topk.__defaults__ = (None, None, loc, mer)

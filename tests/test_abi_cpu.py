@@ -26,7 +26,7 @@ def test_header_and_library_agree(rpx_lib):
     for name in declared:
         assert hasattr(rpx_lib, name), f"{name} declared in include/rpx.h but not exported by librpx.so"
     assert sorted(_native.EXPORTED_SYMBOLS) == declared, "ctypes signature table out of sync with the header"
-    assert rpx_lib.rpx_version() == 100
+    assert rpx_lib.rpx_version() == 200
 
 
 def test_library_has_no_libcuda_dependency():
@@ -57,8 +57,11 @@ def test_host_only_entry_points(rpx_lib):
                            rel_buckets=32, rel_max_distance=128, ln_eps=1e-6)
     assert rpx_lib.rpx_encoder_packed_bytes(C.byref(bad)) == 0
     assert "d_kv" in _native.last_error()
-    assert rpx_lib.rpx_sim_topk_workspace_bytes(1024, 100) > 0
-    assert rpx_lib.rpx_sim_topk_workspace_bytes(1024, 1000) == 0  # k out of range -> loud, not clamped
+    assert rpx_lib.rpx_sim_topk_workspace_bytes(200_000, 1472, 1024, 100) > 0
+    assert rpx_lib.rpx_index_topk_workspace_bytes(200_000, 1472, 1, 100) > 200_000 * 16   # room for the exact pass
+    assert rpx_lib.rpx_index_topk_workspace_bytes(200_000, 1472, 8, 1000) > 0              # k > 200: exact pass only
+    assert rpx_lib.rpx_index_topk_workspace_bytes(200_000, 1472, 8, 5000) == 0             # out of range -> loud, not clamped
+    assert rpx_lib.rpx_index_state_bytes() >= 64
     assert rpx_lib.rpx_encoder_workspace_bytes(None, 1000, 10) == 0
 
 
@@ -79,6 +82,11 @@ def test_compute_fails_loudly_without_gpu(rpx_lib):
     assert rc != _native.RPX_OK
     rc = rpx_lib.rpx_topk_merge(buf, buf, 2, 1, 5, buf, None, buf, None, None)
     assert rc != _native.RPX_OK
+    rc = rpx_lib.rpx_topk_merge_packed(buf, 2, 1, 5, buf, None, buf, None, None)
+    assert rc != _native.RPX_OK
+    h = C.c_void_p()
+    rc = rpx_lib.rpx_index_create(buf, 4, 64, buf, None, C.byref(h))
+    assert rc != _native.RPX_OK and not h.value
 
 
 @needs_no_gpu

@@ -17,12 +17,16 @@ from reprover_b200.dist import ShardedIndex, shard_bounds, sharded_topk
 
 
 def _oracle_local_topk(queries, shard, k, idx_offset, access_mask):
+    """Stand-in for the top-k kernel: the [Q, k, 2] (fp64 score bits, global index) records it writes."""
     words = None if access_mask is None else access_mask.numpy().view(np.uint32)
     s, i, _ = c_oracle.sim_topk(c_oracle.bf16_bits(queries), c_oracle.bf16_bits(shard), k, words, idx_offset)
-    return torch.from_numpy(s), torch.from_numpy(i)
+    return torch.stack([torch.from_numpy(s).view(torch.int64), torch.from_numpy(i)], dim=-1).contiguous()
 
 
-def _oracle_merge(scores64, idx):
+def _oracle_merge(gathered):
+    """Stand-in for rpx_topk_merge_packed on the gathered [world, Q, k, 2] records."""
+    scores64 = gathered[..., 0].contiguous().view(torch.float64)
+    idx = gathered[..., 1].contiguous()
     s, i, c = c_oracle.topk_merge(scores64.numpy(), idx.numpy())
     return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i), torch.from_numpy(c), torch.from_numpy(s)
 

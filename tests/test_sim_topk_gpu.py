@@ -106,8 +106,8 @@ def test_k_larger_than_corpus_and_empty_corpus(rpx_lib, cuda_device):
 
 def test_rejects_unsupported(rpx_lib, cuda_device):
     Q, E = _unit(2, 128, 1, cuda_device), _unit(10, 128, 2, cuda_device)
-    with pytest.raises(_native.RpxError):
-        sim_topk(Q, E, 500)
+    with pytest.raises(ValueError, match="k=5000"):
+        sim_topk(Q, E, 5000)   # validated at the Python boundary with a clear message (k <= 1024)
     with pytest.raises(TypeError):
         sim_topk(Q.float(), E.float(), 5)
 
