@@ -19,7 +19,16 @@ weights (seed 3407).  Every step uses a fresh slice of the corpus; the per-step 
          of Premise objects, then `.cpu()` of the index as retrieval/index.py:37 does): host
          strings -> pinned bytes -> H2D -> engine -> D2H inside the timed region.
   retrieve   extra leg, BASELINE configs[2]/[3]: 1024 states x 200k-premise (per GPU) bf16 index,
-         k = 100, fused sim+top-k (+ all-gather + merge when N > 1): queries/s and roofline.
+         k = 100, fused sim+top-k (+ all-gather + merge when N > 1): queries/s and roofline, plus a
+         `parity` object: 64 sampled queries re-ranked by brute force (fp64 Q.E^T of every rank's shard,
+         all-gathered, exact top-k) against the engine's merged result on EVERY rank — a mismatch makes
+         the run exit non-zero.
+  retrieve_q1 / retrieve_q64   the same index with 1 and 64 states (the reference's production call is one
+         state per retrieve(), retrieval/model.py:338-375): device time, host-to-host time, HBM roofline.
+  retrieve_single (N = 1)  `B200PremiseRetriever.retrieve(state, file, theorem, pos, 100)` host to host on a
+         200k-premise corpus: encode of one state + access bitmask + top-k + Premise objects.
+  sweep (N = 1)  BASELINE configs[4]: encoder throughput at seq_len {128,512,1024,2048} x batch {32,128,512}.
+  reindex_2048 (N = 1)  the shape retrieval/index.py:33 indexes at: max_seq_len 2048, token length ~ U[17, 2048].
 """
 from __future__ import annotations
 
@@ -42,6 +51,15 @@ from reprover_b200 import synth  # noqa: E402
 D_MODEL = 1472
 N_CORPUS = 200_000
 MAX_SEQ_LEN = 512
+
+
+def cpu_threads() -> int:
+    """Host threads of every CPU leg: half the logical CPUs (= the physical cores on these hosts),
+    set explicitly so that a torchrun launch (which exports OMP_NUM_THREADS=1) times the same thing as a
+    plain one."""
+    n = int(os.environ.get("RPX_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(n)
+    return n
 
 
 def encoder_flops(token_lens: np.ndarray) -> float:
@@ -133,9 +151,8 @@ def barrier(world: int):
 def run_engine(args) -> dict:
     from reprover_b200 import _native
     from reprover_b200.corpus import Corpus, File, Pos, Premise
-    from reprover_b200.dist import sharded_topk
     from reprover_b200.engine import T5EncoderEngine
-    from reprover_b200.retrieval_ops import sim_topk
+    from reprover_b200.retrieval_ops import IndexHandle
     from reprover_b200.retriever import B200PremiseRetriever
 
     rank, world, local = dist_env()
@@ -232,14 +249,14 @@ def run_engine(args) -> dict:
         for i in range(W):
             retr.load_corpus(corpora[i])
             retr.reindex_corpus(batch_size=64)
-            host_index = retr.corpus_embeddings.cpu()
+            host_index = retr.corpus_embeddings.to(torch.float32).cpu()
         barrier(world)
         t0 = time.perf_counter()
         e0.record()
         for i in range(W, W + K):
             retr.load_corpus(corpora[i])
             retr.reindex_corpus(batch_size=64)
-            host_index = retr.corpus_embeddings.cpu()   # D2H of the step's result
+            host_index = retr.corpus_embeddings.to(torch.float32).cpu()   # retrieval/index.py:37: fp32 host copy
             lo, hi = step_slices[i]
             h2d += int(offsets[hi] - offsets[lo])
             d2h += host_index.numel() * host_index.element_size()
@@ -253,68 +270,28 @@ def run_engine(args) -> dict:
     else:
         eng_for_retrieve = eng
 
-    # ---- retrieve leg (cfg3 per GPU; cfg4 when world == 8)
-    retrieve = None
+    # ---- retrieve legs (cfg3 per GPU; cfg4 when world == 8; plus the 1- and 64-state shapes)
+    retrieve = retrieve_q1 = retrieve_q64 = None
     if not args.skip_retrieve:
-        nq, n_idx, k = 1024, N_CORPUS, 100
+        n_idx, k = N_CORPUS, 100
         E = synth.random_unit_rows(n_idx, D_MODEL, 1000 + rank, dev)
-        Q = synth.random_unit_rows(nq, D_MODEL, 999, dev)   # same queries on every rank
-        Q_host = Q.cpu().pin_memory()
-        # one retrieve is ~0.6 ms: a handful of repetitions would be timed while the SM clock is still
-        # ramping after the host-side legs; 50 repetitions (~30 ms) after 10 warm-ups are past that
-        reps = max(50, K)
-        warm_r = max(10, W)
-
-        def retrieve_dev():
-            if world == 1:
-                return sim_topk(Q, E, k)
-            return sharded_topk(Q, E, k, row_offset=rank * n_idx)
-
-        for _ in range(warm_r):
-            retrieve_dev()
-        barrier(world)
-        e0.record()
-        for _ in range(reps):
-            retrieve_dev()
-        e1.record()
-        barrier(world)
-        ms_r = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
-        # e2e: queries from pinned host memory, results back to the host
-        res_scores = torch.empty(nq, k, dtype=torch.float32).pin_memory()
-        res_idx = torch.empty(nq, k, dtype=torch.int64).pin_memory()
-
-        def retrieve_host():
-            q = Q_host.to(dev, non_blocking=True)
-            r = sim_topk(q, E, k) if world == 1 else sharded_topk(q, E, k, row_offset=rank * n_idx)
-            res_scores.copy_(r[0], non_blocking=True)
-            res_idx.copy_(r[1], non_blocking=True)
-            torch.cuda.current_stream().synchronize()   # the caller reads the host result here
-
-        for _ in range(3):
-            retrieve_host()   # warm-up (allocator, pinned staging)
-        barrier(world)
-        e0.record()
-        for _ in range(reps):
-            retrieve_host()
-        e1.record()
-        barrier(world)
-        ms_re = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
-        flops = 2.0 * nq * n_idx * D_MODEL
-        bytes_alg = n_idx * D_MODEL * 2 + nq * D_MODEL * 2 + nq * k * 12
-        t_mma = flops / (peaks["tf_burst"] * 1e12)
-        t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
-        retrieve = {
-            "metric": "retrieve queries/s", "config": {"queries": nq, "index_rows_per_gpu": n_idx, "index_rows_total": n_idx * world,
-                                                      "k": k, "dtype": "bf16", "merge": "nccl all_gather + device merge" if world > 1 else "none",
-                                                      "warmup": warm_r, "repetitions": reps},
-            "value": nq / (ms_r / 1e3), "ms": ms_r,
-            "e2e": {"value": nq / (ms_re / 1e3), "ms": ms_re, "h2d_bytes": nq * D_MODEL * 2, "d2h_bytes": nq * k * 12},
-            "roofline": {"bound": "tensor", "achieved": flops / (ms_r / 1e3) / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                         "frac": max(t_mma, t_hbm) / (ms_r / 1e3), "hbm_frac": t_hbm / (ms_r / 1e3),
-                         "note": "whole retrieve (sim kernel + select/rescore [+ gather/merge]) vs max(t_MMA, t_HBM) of the sim kernel"},
-        }
+        handle = IndexHandle(E)
+        Q_all = synth.random_unit_rows(1024, D_MODEL, 999, dev)   # same queries on every rank
+        retrieve = retrieve_leg(Q_all, E, handle, k, rank, world, dev, peaks, e0, e1, K, W, check_parity=True)
+        retrieve_q64 = retrieve_leg(Q_all[:64].contiguous(), E, handle, k, rank, world, dev, peaks, e0, e1, K, W)
+        retrieve_q1 = retrieve_leg(Q_all[:1].contiguous(), E, handle, k, rank, world, dev, peaks, e0, e1, K, W)
+        retrieve["guard"] = handle.stats()
         if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-            retrieve["cpu_baseline"] = cpu_baseline_retrieve(E, Q, k)
+            retrieve["cpu_baseline"] = cpu_baseline_retrieve(E, Q_all, k)
+        del handle, E
+
+    # ---- single-GPU extras: retrieve() as the prover calls it, the config-5 sweep, max_seq_len 2048
+    retrieve_single = sweep = reindex_2048 = None
+    if world == 1 and not args.skip_extras:
+        if e2e is not None:
+            retrieve_single = retrieve_single_leg(retr, dev)
+        sweep = sweep_leg(eng_for_retrieve, dev, peaks)
+        reindex_2048 = reindex_2048_leg(eng_for_retrieve, dev, peaks)
 
     result = {
         "metric": "premises encoded/sec (reindex_corpus, ByT5-small, seq_len<=512)",
@@ -334,12 +311,231 @@ def run_engine(args) -> dict:
                              "note": "algorithmic FLOPs sum F(l_i) of SURVEY 8d over the whole step (per GPU)"},
         "kernel_ms": {k2: v["ms"] for k2, v in prof.items()},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "retrieve": retrieve,
+        "retrieve_q1": retrieve_q1, "retrieve_q64": retrieve_q64, "retrieve_single": retrieve_single,
+        "sweep": sweep, "reindex_2048": reindex_2048,
     }
+    parity = (retrieve or {}).get("parity")
+    if parity is not None and parity["mismatches"] != 0:
+        print(json.dumps(result), flush=True)
+        raise SystemExit(f"[bench] retrieve parity FAILED: {parity}")
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline_encode(cfg, sd, data, offsets, n_premises=args.cpu_sample)
     if world > 1:
         torch.distributed.destroy_process_group()
     return result if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------ retrieve legs
+def brute_force_parity(Q, E, k, rank, world, dev, got_idx, got_s64, n_sample=64):
+    """Checker (not the product): fp64 Q.E^T of this rank's shard for `n_sample` queries, exact local
+    top-(k+8), all-gather, global exact top-k under (score desc, index asc); compared on EVERY rank with
+    the engine's merged result.  fp64 torch sums in another order than the engine's canonical one, so a
+    position only counts as a mismatch when the scores around it differ by more than 1e-12."""
+    nq = Q.shape[0]
+    sel = torch.linspace(0, nq - 1, steps=min(n_sample, nq), device=dev).round().long().unique()
+    S = Q[sel].double() @ E.double().t()                                   # [s, n_idx] fp64
+    top = torch.topk(S, k + 8, dim=1)
+    loc_s, loc_i = top.values, top.indices + rank * E.shape[0]
+    if world > 1:
+        gs = [torch.empty_like(loc_s) for _ in range(world)]
+        gi = [torch.empty_like(loc_i) for _ in range(world)]
+        torch.distributed.all_gather(gs, loc_s)
+        torch.distributed.all_gather(gi, loc_i)
+        loc_s, loc_i = torch.cat(gs, dim=1), torch.cat(gi, dim=1)
+    # order: score desc, index asc (stable sort on index first, then on score)
+    o = torch.argsort(loc_i, dim=1, stable=True)
+    loc_s, loc_i = torch.gather(loc_s, 1, o), torch.gather(loc_i, 1, o)
+    o = torch.argsort(loc_s, dim=1, descending=True, stable=True)
+    want_s, want_i = torch.gather(loc_s, 1, o)[:, :k + 1], torch.gather(loc_i, 1, o)[:, :k + 1]
+    g_i, g_s = got_idx[sel], got_s64[sel]
+    differs = g_i != want_i[:, :k]
+    # a differing position is tolerated only inside a run of (numerically) tied scores
+    gap_ok = (g_s - want_s[:, :k]).abs() < 1e-12
+    mism = int((differs & ~gap_ok).sum())
+    score_err = float((g_s - want_s[:, :k]).abs().max())
+    bad_scores = int(((g_s - want_s[:, :k]).abs() >= 1e-12).sum())
+    out = {"checked_queries": int(sel.numel()), "k": k, "mismatches": mism + bad_scores, "index_positions_differing_within_ties": int((differs & gap_ok).sum()),
+           "max_abs_score_diff": score_err, "checker": "torch fp64 matmul + exact top-k per shard, all-gathered, on every rank"}
+    if world > 1:
+        t = torch.tensor([out["mismatches"]], device=dev)
+        torch.distributed.all_reduce(t)                                   # any rank's mismatch fails the run
+        out["mismatches"] = int(t.item())
+        out["ranks_checked"] = world
+    return out
+
+
+def retrieve_leg(Q, E, handle, k, rank, world, dev, peaks, e0, e1, K, W, check_parity=False):
+    from reprover_b200.dist import sharded_topk
+    from reprover_b200.retrieval_ops import sim_topk
+
+    nq, n_idx = Q.shape[0], E.shape[0]
+    Q_host = Q.cpu().pin_memory()
+    # one retrieve is 0.1-0.6 ms: a handful of repetitions would be timed while the SM clock is still
+    # ramping after the host-side legs; 50 repetitions after 10 warm-ups are past that
+    reps, warm_r = max(50, K), max(10, W)
+
+    def retrieve_dev(q=Q):
+        if world == 1:
+            return sim_topk(q, handle, k, want_scores64=True)
+        s32, idx, cnt, s64 = sharded_topk(q, handle, k, row_offset=rank * n_idx)
+        return s32, idx, cnt, s64
+
+    for _ in range(warm_r):
+        retrieve_dev()
+    barrier(world)
+    e0.record()
+    for _ in range(reps):
+        retrieve_dev()
+    e1.record()
+    barrier(world)
+    ms_r = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
+    # e2e: queries from pinned host memory, results back to the host
+    res_scores = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+    res_idx = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+
+    def retrieve_host():
+        r = retrieve_dev(Q_host.to(dev, non_blocking=True))
+        res_scores.copy_(r[0], non_blocking=True)
+        res_idx.copy_(r[1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the host result here
+
+    for _ in range(3):
+        retrieve_host()   # warm-up (allocator, pinned staging)
+    barrier(world)
+    e0.record()
+    for _ in range(reps):
+        retrieve_host()
+    e1.record()
+    barrier(world)
+    ms_re = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
+    flops = 2.0 * nq * n_idx * D_MODEL
+    bytes_alg = n_idx * D_MODEL * 2 + nq * D_MODEL * 2 + nq * k * 12
+    t_mma = flops / (peaks["tf_burst"] * 1e12)
+    t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_mma > t_hbm else "hbm"
+    leg = {
+        "metric": "retrieve queries/s", "config": {"queries": nq, "index_rows_per_gpu": n_idx, "index_rows_total": n_idx * world,
+                                                  "k": k, "dtype": "bf16", "merge": "nccl all_gather + device merge" if world > 1 else "none",
+                                                  "path": "streaming kernel (HBM-bound)" if nq <= 2 else "tcgen05 MMA + fused top-k",
+                                                  "warmup": warm_r, "repetitions": reps, "l2": "index (589 MB) larger than L2"},
+        "value": nq / (ms_r / 1e3), "ms": ms_r,
+        "e2e": {"value": nq / (ms_re / 1e3), "ms": ms_re, "h2d_bytes": nq * D_MODEL * 2, "d2h_bytes": nq * k * 12},
+        "roofline": {"bound": bound,
+                     "achieved": (flops / (ms_r / 1e3) / 1e12) if bound == "tensor" else (bytes_alg / (ms_r / 1e3) / 1e9),
+                     "peak": peaks["tf_burst"] if bound == "tensor" else peaks["hbm_gbs"],
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                     "frac": max(t_mma, t_hbm) / (ms_r / 1e3), "hbm_frac": t_hbm / (ms_r / 1e3),
+                     "algorithmic_bytes": bytes_alg, "peak_source": peaks["source"],
+                     "note": "whole retrieve (every launch of the call [+ all-gather + merge]) vs max(t_MMA, t_HBM) of one pass over the index"},
+    }
+    if check_parity:
+        r = retrieve_dev()
+        torch.cuda.synchronize()
+        leg["parity"] = brute_force_parity(Q, E, k, rank, world, dev, r[1], r[3])
+    return leg
+
+
+def retrieve_single_leg(retr, dev):
+    """`retrieve()` host to host, one state per call, on a 200k-premise corpus split into 2000 files
+    (a chain of imports, so the access bitmask is a real one)."""
+    from reprover_b200.corpus import Corpus, File, Pos, Premise
+
+    N, n_files = N_CORPUS, 2000
+    files = []
+    for f in range(n_files):
+        prem = [Premise(f"F{f}.lean", f"F{f}.p{j}", Pos(j + 1, 0), Pos(j + 1, 5), f"theorem p{j} : True := trivial")
+                for j in range(N // n_files)]
+        files.append((File(f"F{f}.lean", prem), [f"F{f - 1}.lean"] if f else []))
+    retr.load_corpus(Corpus.from_files(files))
+    retr.corpus_embeddings = synth.random_unit_rows(N, D_MODEL, 7, dev)   # latency does not depend on the values
+    retr.embeddings_staled = False
+    sdat, soff = synth.synth_states(80, seed=5, min_len=50, max_len=400)
+    states = [s.decode() for s in synth.split_strings(sdat, soff)]
+    where = (f"F{n_files - 1}.lean", "t", Pos(50, 0))
+    for st in states[:16]:
+        retr.retrieve(st, *where, 100)
+    torch.cuda.synchronize()
+    lat = []
+    for st in states[16:]:
+        t0 = time.perf_counter()
+        prem, sc = retr.retrieve(st, *where, 100)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    assert len(prem) == 100
+    return {"metric": "retrieve() latency, one state per call, host to host", "unit": "ms",
+            "median": float(np.median(lat)), "p90": float(np.percentile(lat, 90)), "min": float(min(lat)), "calls": len(lat),
+            "config": {"index_rows": N, "files": n_files, "k": 100, "state_bytes": "U[50,400]", "max_seq_len": retr.max_seq_len,
+                       "accessible_rows": int(N - N // n_files + 49)}}
+
+
+def sweep_leg(eng, dev, peaks):
+    """BASELINE configs[4]: seq_len {128,512,1024,2048} x batch {32,128,512}, ids ~ U[3,258], full-length
+    rows, device-timed with CUDA events, 3 warm-ups per point."""
+    rng = np.random.default_rng(synth.SEED)
+    rows = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for L in (128, 512, 1024, 2048):
+        for B in (32, 128, 512):
+            data = rng.integers(0, 256, size=B * (L - 1), dtype=np.uint8)   # ids 3..258 = bytes 0..255, + EOS
+            offsets = np.arange(B + 1, dtype=np.int64) * (L - 1)
+            d = torch.from_numpy(data).to(dev)
+            out = torch.empty(B, D_MODEL, dtype=torch.bfloat16, device=dev)
+            per_call = max(1, eng.max_tokens_per_call // L)
+
+            def step():
+                for a in range(0, B, per_call):
+                    b = min(B, a + per_call)
+                    eng.encode_packed_bytes(d[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], L, out[a:b])
+
+            for _ in range(3):
+                step()
+            reps = max(2, min(20, int(4e5 // (B * L))))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            tf = B * L * (434_110_464.0 + 18_432.0 * L) / ms / 1e9
+            rows.append({"seq_len": L, "batch": B, "ms": ms, "seq_per_s": B / ms * 1e3, "tflops": tf,
+                         "frac_of_sustained_peak": tf / peaks["tf_sustained"], "reps": reps})
+    return {"metric": "encoder sequences/s and roofline fraction, BASELINE configs[4]", "peak": peaks["tf_sustained"],
+            "peak_source": peaks["source"] + " (sustained bf16)", "rows": rows,
+            "frac_min": min(r["frac_of_sustained_peak"] for r in rows), "frac_max": max(r["frac_of_sustained_peak"] for r in rows)}
+
+
+def reindex_2048_leg(eng, dev, peaks, P=2048):
+    """The shape the reference indexes at (retrieval/index.py:33: max_seq_len 2048): byte length ~ U[16, 2047]."""
+    data, offsets = synth.synth_premises(P * 3, seed=synth.SEED + 7, min_len=16, max_len=2047)
+    tok = np.minimum(np.diff(offsets) + 1, 2048)
+    d_data = torch.from_numpy(data.copy()).to(dev)
+    out = torch.empty(P, D_MODEL, dtype=torch.bfloat16, device=dev)
+
+    def step(i):
+        lo, hi = i * P, (i + 1) * P
+        cum = np.concatenate([[0], np.cumsum(tok[lo:hi])])
+        a = 0
+        while a < P:
+            b = int(np.searchsorted(cum, cum[a] + eng.max_tokens_per_call, side="right")) - 1
+            b = min(max(b, a + 1), P)
+            b0, b1 = int(offsets[lo + a]), int(offsets[lo + b])
+            eng.encode_packed_bytes(d_data[b0:b1], offsets[lo + a:lo + b + 1] - b0, 2048, out[a:b])
+            a = b
+
+    step(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    step(1)
+    step(2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    fl = encoder_flops(tok[P:3 * P]) / 2
+    tf = fl / ms / 1e9
+    return {"metric": "premises encoded/sec at max_seq_len 2048", "value": P / ms * 1e3, "unit": "premises/s", "ms_per_step": ms,
+            "config": {"premises_per_step": P, "token_len": "U[17,2048]", "tokens_per_step": int(tok[P:3 * P].sum() // 2), "warmup_steps": 1, "steps": 2},
+            "encoder_roofline": {"achieved_tflops": tf, "peak": peaks["tf_sustained"], "frac": tf / peaks["tf_sustained"]}}
 
 
 # ------------------------------------------------------------------------------------------ CPU reference
@@ -349,6 +545,7 @@ def cpu_baseline_encode(cfg, sd, data, offsets, n_premises: int, precision: str 
     retrieval/model.py:26 sets it.  Bounded sample; this is the oracle used as a stopwatch."""
     from oracle import reference_path as ref
 
+    cpu_threads()
     torch.set_float32_matmul_precision(precision)
     enc = ref.build_hf_encoder(cfg, sd)
     tok = ref.build_hf_tokenizer()
@@ -368,6 +565,7 @@ def cpu_baseline_retrieve(E_dev: torch.Tensor, Q_dev: torch.Tensor, k: int, n_qu
     .tolist(), Python walk) for a bounded sample of the same queries against the same index."""
     from oracle import reference_path as ref
 
+    cpu_threads()
     torch.set_float32_matmul_precision("medium")
     E = E_dev.float().cpu()
     Q = Q_dev[:n_queries].float().cpu()
@@ -392,6 +590,7 @@ def run_reference(args) -> dict:
     S = args.reference_premises_per_step
     cfg = dict(synth.BYT5_SMALL)
     sd = synth.random_t5_state_dict(cfg, seed=synth.SEED)
+    cpu_threads()
     torch.set_float32_matmul_precision("medium")  # retrieval/model.py:26
     enc = ref.build_hf_encoder(cfg, sd)
     tok = ref.build_hf_tokenizer()
@@ -432,6 +631,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-retrieve", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip retrieve_single / sweep / reindex_2048 (N = 1 legs)")
     ap.add_argument("--tmp", default="/tmp/rpx_bench")
     args = ap.parse_args()
     if args.impl == "engine" and args.warmup < 3:

@@ -181,7 +181,7 @@ int rpx_index_destroy(rpx_index* ix);
 int rpx_index_stats(rpx_index* ix, void* stream, float* h_norm_max, float* h_max_err, float* h_max_eps,
                     int64_t* h_n_exact);
 
-/* Path selection flags of rpx_index_topk (0 = automatic: streaming kernel for nq <= 4, tcgen05
+/* Path selection flags of rpx_index_topk (0 = automatic: streaming kernel for nq <= 2, tcgen05
  * kernel otherwise, exact pass for k > 200).  The forcing flags exist for parity tests. */
 enum { RPX_TOPK_AUTO = 0, RPX_TOPK_FORCE_MMA = 1, RPX_TOPK_FORCE_STREAM = 2, RPX_TOPK_FORCE_EXACT = 4 };
 

@@ -71,26 +71,49 @@ def _premise(p: Any) -> Premise:
     return Premise(p.path, p.full_name, _pos(p.start), _pos(p.end), p.code)
 
 
-def convert_corpus(ref: Any) -> Corpus:
-    """`common.Corpus` stand-in -> `reprover_b200.corpus.Corpus` with the same `all_premises` order."""
+def _file_order(ref: Any) -> List[str]:
+    """File order for the converted corpus: every file after the files it imports, and the files that
+    hold premises in the order `all_premises` lists them.
+
+    The reference adds graph nodes in `corpus.jsonl` order, which is an import order (it asserts that every
+    import is already a node, common.py:211-213), and networkx keeps insertion order through
+    `transitive_closure_dag` — so the graph's own node order is the natural choice and also places files
+    WITHOUT premises (which `all_premises` cannot reveal) correctly.  If a pickle's node order has been
+    disturbed, fall back to a topological order that keeps the premise-bearing files in sequence."""
     g = ref.transitive_dep_graph
-    order: List[str] = []
-    seen = set()
+    nodes = list(g.nodes)
+    rank = {path: i for i, path in enumerate(nodes)}
+    if all(rank[dep] < rank[path] for path in nodes for dep in g.successors(path)):
+        return nodes
+    seen, with_premises = set(), []
     for p in ref.all_premises:
         if p.path not in seen:
             seen.add(p.path)
-            order.append(p.path)
-    order += [n for n in g.nodes if n not in seen]
-    # a file may only import files that precede it; a topological order of the DAG guarantees that
-    # while the premise order inside each file is kept.  The reference builds all_premises in file
-    # (= topological) order (common.py:202-215), so `order` normally already satisfies it.
-    rank = {path: i for i, path in enumerate(order)}
-    for path in order:
-        for dep in g.successors(path):
-            if rank[dep] > rank[path]:
-                raise ValueError(f"reference corpus is not in import order: {path} imports {dep}")
+            with_premises.append(p.path)
+    order: List[str] = []
+    placed = set()
+
+    def place(path: str, stack: tuple) -> None:
+        if path in placed:
+            return
+        if path in stack:
+            raise ValueError(f"reference corpus has an import cycle through {path}")
+        for dep in g.successors(path):        # imports first (empty files are pulled in here)
+            place(dep, stack + (path,))
+        placed.add(path)
+        order.append(path)
+
+    for path in with_premises + [n for n in nodes if n not in seen]:
+        place(path, ())
+    return order
+
+
+def convert_corpus(ref: Any) -> Corpus:
+    """`common.Corpus` (the reference's own object or the unpickler's stand-in) ->
+    `reprover_b200.corpus.Corpus` with the same `all_premises` order."""
+    g = ref.transitive_dep_graph
     files = []
-    for path in order:
+    for path in _file_order(ref):
         premises = [_premise(p) for p in g.nodes[path]["file"].premises]
         files.append((File(path, premises), list(g.successors(path))))
     corpus = Corpus.from_files(files)
@@ -110,3 +133,92 @@ def load_reference_index(path_or_bytes) -> IndexedCorpus:
     with fh:
         ref = _Unpickler(fh).load()
     return IndexedCorpus(convert_corpus(ref.corpus), ref.embeddings)
+
+
+# ------------------------------------------------------------------------------------------ export
+# The other direction: an index built by this engine, written so that a STOCK checkout of the
+# reference loads it — `pickle.load` at retrieval/model.py:81-85 must find `common.IndexedCorpus`,
+# `common.Corpus` (attributes `transitive_dep_graph`: networkx DiGraph, transitive closure, node
+# attribute "file"; `all_premises`; `imported_premises_cache`, common.py:181-224), `common.File`,
+# `common.Premise` and `lean_dojo.Pos` (`from lean_dojo import Pos`, common.py:14), with fp32 CPU
+# embeddings (common.py:336-338).  When this process runs inside the reference tree the real classes
+# are used; otherwise stand-ins are registered under those module names for the duration of the dump
+# (pickle stores classes by module + qualified name, and instances as NEWOBJ + attribute dict, which is
+# what the reference's dataclasses produce).
+import contextlib
+import sys
+import types
+
+
+def _stand_in(module: str, name: str) -> type:
+    cls = type(name, (), {})
+    cls.__module__, cls.__qualname__ = module, name
+    return cls
+
+
+@contextlib.contextmanager
+def _reference_classes():
+    """Yield {"IndexedCorpus", "Corpus", "File", "Premise", "Pos"} -> classes that pickle under the
+    reference's names."""
+    common = sys.modules.get("common")
+    lean_dojo = sys.modules.get("lean_dojo")
+    if (common is not None and lean_dojo is not None and hasattr(lean_dojo, "Pos")
+            and all(hasattr(common, n) for n in ("IndexedCorpus", "Corpus", "File", "Premise"))):
+        yield {n: getattr(common, n) for n in ("IndexedCorpus", "Corpus", "File", "Premise")} | {"Pos": lean_dojo.Pos}
+        return
+    added = []
+    try:
+        classes = {n: _stand_in("common", n) for n in ("IndexedCorpus", "Corpus", "File", "Premise")}
+        classes["Pos"] = _stand_in("lean_dojo", "Pos")
+        for mod_name, names in (("common", ("IndexedCorpus", "Corpus", "File", "Premise")), ("lean_dojo", ("Pos",))):
+            if mod_name in sys.modules:
+                raise RuntimeError(f"a module named {mod_name!r} that is not the reference's is loaded; cannot write "
+                                   f"the reference index layout from this process")
+            m = types.ModuleType(mod_name)
+            for n in names:
+                setattr(m, n, classes[n])
+            sys.modules[mod_name] = m
+            added.append(mod_name)
+        yield classes
+    finally:
+        for mod_name in added:
+            sys.modules.pop(mod_name, None)
+
+
+def _raw(cls: type, **attrs) -> Any:
+    """An instance of `cls` with exactly these attributes, bypassing __init__ / frozen dataclasses."""
+    obj = object.__new__(cls)
+    obj.__dict__.update(attrs)
+    return obj
+
+
+def dump_reference_index(corpus: Corpus, embeddings, fh) -> None:
+    """Write `IndexedCorpus(corpus, embeddings)` to the binary file `fh` in the reference's layout."""
+    import networkx as nx
+    import torch
+
+    emb = embeddings.detach().to(torch.float32).cpu().contiguous()
+    assert emb.shape[0] == len(corpus), "one embedding row per premise"
+    with _reference_classes() as ref:
+        conv = {}
+
+        def premise(p: Premise):
+            q = conv.get(id(p))
+            if q is None:
+                q = _raw(ref["Premise"], path=p.path, full_name=p.full_name,
+                         start=_raw(ref["Pos"], line_nb=int(p.start.line_nb), column_nb=int(p.start.column_nb)),
+                         end=_raw(ref["Pos"], line_nb=int(p.end.line_nb), column_nb=int(p.end.column_nb)), code=p.code)
+                conv[id(p)] = q
+            return q
+
+        g = nx.DiGraph()
+        for f in corpus.files:
+            g.add_node(f.path, file=_raw(ref["File"], path=f.path, premises=[premise(p) for p in f.premises]))
+        for f in corpus.files:
+            for dep in corpus.get_dependencies(f.path):    # already the transitive closure
+                g.add_edge(f.path, dep)
+        # `imported_premises_cache` is filled lazily by the reference (common.py:262-273): an empty one is a
+        # valid state and keeps a mathlib-sized pickle from carrying every file's transitive premise list
+        ref_corpus = _raw(ref["Corpus"], transitive_dep_graph=g, all_premises=[premise(p) for p in corpus.all_premises],
+                          imported_premises_cache={})
+        pickle.dump(_raw(ref["IndexedCorpus"], corpus=ref_corpus, embeddings=emb), fh, protocol=4)

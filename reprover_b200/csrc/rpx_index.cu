@@ -5,7 +5,7 @@
 // retrieve().  Creating the handle runs the one pass that depends only on the matrix (the row-norm
 // bound of the exactness guard); `rpx_index_topk` is `Corpus.get_nearest_premises`' device half
 // (common.py:307-322) and picks one of three paths:
-//     nq <= 4            rpx_smallq.cu   one HBM-bound streaming kernel (the reference's real call: nq = 1)
+//     nq <= 2            rpx_smallq.cu   one HBM-bound streaming kernel (the reference's real call: nq = 1)
 //     otherwise          rpx_simtopk.cu  tcgen05 MMA with the top-k fused into the epilogue
 //     k > 200 or flagged rpx_exact.cu    exact fp64 pass (always launched; returns at once if idle)
 #include <stdlib.h>
@@ -32,8 +32,12 @@ constexpr int kMaxSmsForSizing = 160;  // workspace queries work without a devic
 int small_q_max() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("RPX_SMALLQ_MAX");  // tuning knob: largest nq routed to the streaming kernel (0..4)
-    v = e ? atoi(e) : 4;
+    // Largest nq routed to the streaming kernel (0..4; RPX_SMALLQ_MAX overrides).  Measured on B200, 200k x 1472,
+    // k = 100 (tools/topk_bench.py): nq = 1  0.121 ms streaming vs 0.194 ms tcgen05;  nq = 2  0.162 vs 0.175;
+    // nq = 3 (two passes)  0.280 vs 0.181;  nq = 4  0.260 vs 0.179 (the FMA work of four queries per index
+    // byte is what a tensor core is for).
+    const char* e = getenv("RPX_SMALLQ_MAX");
+    v = e ? atoi(e) : 2;
     if (v < 0) v = 0;
     if (v > 4) v = 4;
   }

@@ -71,9 +71,13 @@ def sharded_topk(queries: torch.Tensor, local_shard, k: int, row_offset: int,
 class ShardedIndex:
     """This rank's slice of a row-sharded embedding index."""
 
-    def __init__(self, n_rows_total: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> None:
-        self.world_size = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
+    def __init__(self, n_rows_total: int, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 group=None) -> None:
+        """Rank / world size default to those of `group` (the default process group when None); the index
+        remembers the group, so bounds, the all-gather and the merge always talk about the same ranks."""
+        self.group = group
+        self.world_size = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.bounds = shard_bounds(n_rows_total, self.world_size)
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.embeddings: Optional[torch.Tensor] = None
@@ -87,7 +91,11 @@ class ShardedIndex:
 
     def topk(self, queries: torch.Tensor, k: int, access_mask: Optional[torch.Tensor] = None, **kw):
         assert self.embeddings is not None
-        return sharded_topk(queries, self.embeddings, k, self.lo, access_mask=access_mask, **kw)
+        group = kw.pop("group", self.group)
+        if dist.is_initialized():
+            assert dist.get_world_size(group) == self.world_size, (
+                f"index cut for {self.world_size} ranks but the collective runs over {dist.get_world_size(group)}")
+        return sharded_topk(queries, self.embeddings, k, self.lo, access_mask=access_mask, group=group, **kw)
 
     # ------------------------------------------------------------------ on-disk form
     # A directory: `manifest.json` (row bounds, dtype, width), one `embeddings.<r>-of-<R>.pt` per
@@ -114,7 +122,7 @@ class ShardedIndex:
                 with open(os.path.join(directory, "corpus.pickle"), "wb") as fh:
                     pickle.dump(corpus, fh)
         if dist.is_initialized() and self.world_size > 1:
-            dist.barrier(group=group)   # the directory is complete when any rank returns
+            dist.barrier(group=group if group is not None else self.group)   # the directory is complete when any rank returns
 
     @classmethod
     def load(cls, directory: str, rank: Optional[int] = None, world_size: Optional[int] = None,
@@ -151,6 +159,8 @@ class ShardedIndex:
         buf = torch.zeros(longest, self.embeddings.shape[1], dtype=self.embeddings.dtype, device=self.embeddings.device)
         buf[: self.hi - self.lo] = self.embeddings
         out = torch.empty((self.world_size * longest, buf.shape[1]), dtype=buf.dtype, device=buf.device)
+        group = group if group is not None else self.group
+        assert dist.get_world_size(group) == self.world_size
         dist.all_gather_into_tensor(out, buf, group=group)
         if self.rank != dst:
             return None

@@ -31,19 +31,58 @@ _LAYER_KEYS = {
 _REL_BIAS_KEY = "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"
 
 
+def resolve_checkpoint_dir(name_or_path: str) -> str:
+    """A local HF checkpoint directory for `name_or_path`.
+
+    The reference hands the string to `AutoModelForTextEncoding.from_pretrained` (retrieval/model.py:45),
+    which also accepts hub ids such as `kaiyuy/leandojo-lean4-retriever-byt5-small`.  A directory is used
+    as it is; a hub id is resolved through the local HF cache (`huggingface_hub.snapshot_download`, which
+    only touches the network when the snapshot is not cached).  Anything else fails here, with the reason,
+    instead of deep inside the loader."""
+    if os.path.isdir(name_or_path):
+        return name_or_path
+    if os.path.exists(name_or_path):
+        raise FileNotFoundError(f"{name_or_path!r} is a file; an HF checkpoint DIRECTORY (config.json + "
+                                f"model.safetensors / pytorch_model.bin) or a hub id is expected")
+    try:
+        from huggingface_hub import snapshot_download
+
+        return snapshot_download(name_or_path, allow_patterns=["config.json", "*.safetensors", "pytorch_model.bin",
+                                                               "*.json", "*.txt", "*.model"])
+    except Exception as exc:  # no network / not cached / not a repo id
+        raise FileNotFoundError(
+            f"{name_or_path!r} is neither a local checkpoint directory nor a hub snapshot available to this "
+            f"machine ({type(exc).__name__}: {exc}). Download the checkpoint and pass its directory.") from exc
+
+
 def load_hf_checkpoint(path: str) -> Tuple[Dict, Dict[str, torch.Tensor]]:
-    """(config dict, fp32 CPU state dict) from an HF checkpoint directory
+    """(config dict, fp32 CPU state dict) from an HF checkpoint directory or hub id
     (`config.json` + `model.safetensors` or `pytorch_model.bin`)."""
-    with open(os.path.join(path, "config.json")) as fh:
+    path = resolve_checkpoint_dir(path)
+    cfg_path = os.path.join(path, "config.json")
+    if not os.path.exists(cfg_path):
+        raise FileNotFoundError(f"{path}: no config.json — not an HF checkpoint directory")
+    with open(cfg_path) as fh:
         cfg = json.load(fh)
     st_path = os.path.join(path, "model.safetensors")
+    bin_path = os.path.join(path, "pytorch_model.bin")
     if os.path.exists(st_path):
         from safetensors.torch import load_file
 
         sd = load_file(st_path)
+    elif os.path.exists(bin_path):
+        sd = torch.load(bin_path, map_location="cpu", weights_only=True)
     else:
-        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+        raise FileNotFoundError(f"{path}: neither model.safetensors nor pytorch_model.bin")
     return cfg, {k: v.float() for k, v in sd.items()}
+
+
+def required_weight_keys(config: Dict) -> List[str]:
+    """Every state-dict key the encoder engine reads (HF T5EncoderModel names)."""
+    keys = [_REL_BIAS_KEY, "encoder.final_layer_norm.weight"]
+    for i in range(int(config["num_layers"])):
+        keys += [pattern.format(i=i) for pattern in _LAYER_KEYS.values()]
+    return keys
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -61,6 +100,14 @@ class T5EncoderEngine:
             raise RuntimeError(
                 f"T5EncoderEngine needs a CUDA device (got {self.device}); this engine has no CPU path")
         self.config = dict(config)
+        missing = [k for k in required_weight_keys(config) if k not in state_dict]
+        if "shared.weight" not in state_dict and "encoder.embed_tokens.weight" not in state_dict:
+            missing.insert(0, "shared.weight (or encoder.embed_tokens.weight)")
+        if missing:
+            raise KeyError(f"checkpoint is not a T5/ByT5 encoder state dict: {len(missing)} weights missing, "
+                           f"first: {missing[:3]}")
+        # kept (by reference, no copy) so that save_pretrained can write the checkpoint back out
+        self._state_dict = state_dict
         if config.get("feed_forward_proj", "gated-gelu") != "gated-gelu":
             raise NotImplementedError("only the gated-gelu T5 v1.1 / ByT5 feed-forward is implemented")
         self.hidden_size = int(config["d_model"])
@@ -119,6 +166,24 @@ class T5EncoderEngine:
             self.close()
         except Exception:
             pass
+
+    def save_pretrained(self, save_directory: str) -> None:
+        """`encoder.save_pretrained(dir)` as the reference's callers use it (generation/model.py:224-226
+        saves the retriever's encoder next to the generator): writes `config.json` and
+        `model.safetensors` with the fp32 weights this engine was built from, loadable by
+        `AutoModelForTextEncoding.from_pretrained(dir)` and by `load_hf`."""
+        from safetensors.torch import save_file
+
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(self.config)
+        cfg.setdefault("architectures", ["T5EncoderModel"])
+        cfg.setdefault("model_type", "t5")
+        with open(os.path.join(save_directory, "config.json"), "w") as fh:
+            json.dump(cfg, fh, indent=1)
+        sd = self._state_dict
+        tensors = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in sd.items()
+                   if k != "encoder.embed_tokens.weight" or "shared.weight" not in sd}
+        save_file(tensors, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
 
     @classmethod
     def from_hf_dir(cls, path: str, device, **kw) -> "T5EncoderEngine":

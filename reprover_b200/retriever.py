@@ -39,8 +39,10 @@ class _Serialized:
 class B200PremiseRetriever:
     def __init__(self, model_name: str, lr: float = 0.0, warmup_steps: int = 0, max_seq_len: int = 2048,
                  num_retrieved: int = 100, device: Union[int, str, torch.device, None] = None,
-                 dtype: Optional[torch.dtype] = None, max_tokens_per_call: int = 1 << 18) -> None:
-        """`model_name` is an HF checkpoint directory (config.json + model.safetensors)."""
+                 dtype: Optional[torch.dtype] = None, max_tokens_per_call: int = 1 << 18,
+                 output_dtype: Optional[torch.dtype] = None) -> None:
+        """`model_name` is an HF checkpoint directory (config.json + model.safetensors) or a hub id that
+        is available in the local HF cache."""
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
         device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
@@ -55,22 +57,54 @@ class B200PremiseRetriever:
         self.num_retrieved = num_retrieved
         self.max_seq_len = max_seq_len
         self.device = device
-        # reference dtype policy (retrieval/model.py:56-66): bf16 on GPUs with cc >= 8 unless told otherwise.
-        # The engine always computes with bf16 operands / fp32 accumulation; `dtype` selects the dtype of
-        # the embeddings it hands back.
-        self.dtype = torch.bfloat16 if dtype is None else dtype
+        # Reference dtype policy (retrieval/model.py:56-66): bf16 on GPUs with cc >= 8 unless told
+        # otherwise — on a B200 that is bf16, which is the one compute dtype this engine has (bf16
+        # operands, fp32 accumulation, fp32 residual stream; similarity index held in bf16 like the
+        # reference's GPU path, :363-366).  `dtype=torch.float32` in the reference means an fp32 MODEL
+        # and an fp32 index; quietly running bf16 under that name would misreport what was computed, so
+        # it is refused.  `output_dtype=torch.float32` is the separate, honest knob: same computation,
+        # embeddings handed back as fp32 tensors.
+        if dtype not in (None, torch.bfloat16):
+            raise NotImplementedError(
+                f"dtype={dtype}: this engine computes in bf16 (fp32 accumulation) only — the reference's own "
+                f"default on this GPU. Pass dtype=None / torch.bfloat16; use output_dtype=torch.float32 to get "
+                f"the embeddings as fp32 tensors.")
+        self.dtype = torch.bfloat16 if output_dtype is None else output_dtype
         if self.dtype not in (torch.bfloat16, torch.float32):
-            raise NotImplementedError(f"embedding dtype {self.dtype} is not supported (bf16 or fp32)")
+            raise NotImplementedError(f"output dtype {self.dtype} is not supported (bf16 or fp32)")
+        self.model_name = model_name
         cfg, sd = load_hf_checkpoint(model_name)
         self.encoder = T5EncoderEngine(cfg, sd, device, max_tokens_per_call=max_tokens_per_call)
         self.corpus: Optional[Corpus] = None
         self.corpus_embeddings: Optional[torch.Tensor] = None
         self.embeddings_staled = True
+        self.sharded_index = None
+        self._tokenizer = None
+        self._index_handle = None      # rpx_index over the bf16 copy of corpus_embeddings
+        self._index_source = None      # (tensor identity, version) the handle was built from
 
     # ------------------------------------------------------------------ construction (reference :52-85)
     @classmethod
     def load_hf(cls, ckpt_path: str, max_seq_len: int, device, dtype=None) -> "B200PremiseRetriever":
         return cls(ckpt_path, 0.0, 0, max_seq_len, 100, device=device, dtype=dtype)
+
+    @property
+    def tokenizer(self):
+        """The HF `ByT5Tokenizer` the reference keeps in `self.tokenizer` (retrieval/model.py:44); its
+        callers only persist it (`generation/model.py:224-226`: `retriever.tokenizer.save_pretrained(dir)`).
+        The engine itself tokenises on the device (`rpx_encode_bytes`) and never calls this object."""
+        if self._tokenizer is None:
+            try:
+                from transformers import AutoTokenizer, ByT5Tokenizer
+            except ImportError as exc:  # pragma: no cover
+                raise RuntimeError("`retriever.tokenizer` needs the `transformers` package") from exc
+            try:
+                from .engine import resolve_checkpoint_dir
+
+                self._tokenizer = AutoTokenizer.from_pretrained(resolve_checkpoint_dir(self.model_name))
+            except Exception:
+                self._tokenizer = ByT5Tokenizer()   # the checkpoint ships no tokenizer files: ByT5's is parameter-free
+        return self._tokenizer
 
     def load_corpus(self, path_or_corpus: Union[str, Corpus]) -> None:
         """Attach a corpus: a `Corpus`, a `corpus.jsonl` path (stale index) or a pickled
@@ -87,15 +121,20 @@ class B200PremiseRetriever:
             self.corpus_embeddings = None
             self.embeddings_staled = True
         else:
+            from .compat import convert_corpus, load_reference_index
+
             try:
                 with open(path, "rb") as fh:
                     indexed = pickle.load(fh)
             except (ModuleNotFoundError, AttributeError):
-                # an index written by the reference itself (classes from `common` / `lean_dojo`)
-                from .compat import load_reference_index
-
+                # an index in the reference's layout (classes from `common` / `lean_dojo`), read without them
                 indexed = load_reference_index(path)
-            self.corpus = indexed.corpus
+            corpus = indexed.corpus
+            if not isinstance(corpus, Corpus):
+                # inside the reference tree `common` IS importable and pickle.load hands back the reference's
+                # own Corpus: convert it, or retrieval would silently run the reference's torch code
+                corpus = convert_corpus(corpus)
+            self.corpus = corpus
             self.corpus_embeddings = indexed.embeddings
             self.embeddings_staled = False
 
@@ -188,13 +227,36 @@ class B200PremiseRetriever:
         reference :215-225, 281-289)."""
         self.reindex_corpus(batch_size=32)
         ctxs = [Context(f, t, Pos.from_any(p), s) for s, f, t, p in zip(states, file_names, theorem_full_names, theorem_poses)]
+        if not isinstance(k, int) or k < 1:
+            raise ValueError(f"k={k!r}: retrieve() needs a positive number of premises")
         context_emb = self.encode_texts([c.serialize() for c in ctxs])
-        if self.corpus_embeddings.device != context_emb.device:
-            self.corpus_embeddings = self.corpus_embeddings.to(context_emb.device)
-        if self.corpus_embeddings.dtype != torch.bfloat16:
-            # the reference casts the index to the query dtype (bf16 on GPU) on first use (:363-366)
-            self.corpus_embeddings = self.corpus_embeddings.to(torch.bfloat16)
-        return self.corpus.get_nearest_premises(self.corpus_embeddings, ctxs, context_emb, k)
+        return self.corpus.get_nearest_premises(self.index_handle(), ctxs, context_emb, k)
+
+    def index_handle(self):
+        """The engine's handle on the similarity index: the bf16 device copy of `corpus_embeddings`
+        (the reference moves / casts the index to the query's device and dtype on first use, :363-366 —
+        bf16 on this GPU) plus the state derived from it once.  Rebuilt when `corpus_embeddings` is replaced
+        or modified in place."""
+        from .retrieval_ops import IndexHandle
+
+        emb = self.corpus_embeddings
+        assert emb is not None, "no index: load_corpus + reindex_corpus first"
+        src = (id(emb), emb._version)
+        if self._index_handle is None or self._index_source != src:
+            if emb.device != self.device or emb.dtype != torch.bfloat16:
+                if self.dtype == torch.bfloat16:
+                    # like the reference, keep the index on the query's device in the query's dtype
+                    self.corpus_embeddings = emb = emb.to(device=self.device, dtype=torch.bfloat16)
+                    bf16 = emb
+                else:
+                    bf16 = emb.to(device=self.device, dtype=torch.bfloat16)   # fp32 stays what the caller sees
+            else:
+                bf16 = emb
+            if self._index_handle is not None:
+                self._index_handle.close()
+            self._index_handle = IndexHandle(bf16)
+            self._index_source = (id(self.corpus_embeddings), self.corpus_embeddings._version)
+        return self._index_handle
 
     # ------------------------------------------------------------------ row-sharded index (SURVEY §8e)
     # One process per GPU, `torch.distributed` initialised by the caller.  `reindex_corpus_sharded`
@@ -207,9 +269,10 @@ class B200PremiseRetriever:
 
         assert self.corpus is not None, "load_corpus first"
         index = getattr(self, "sharded_index", None)
-        if index is not None and index.embeddings is not None and index.bounds[-1] == len(self.corpus):
+        if index is not None and index.embeddings is not None and index.bounds[-1] == len(self.corpus) \
+                and index.group is group:
             return index
-        index = ShardedIndex(len(self.corpus))
+        index = ShardedIndex(len(self.corpus), group=group)
         premises = self.corpus.all_premises[index.lo:index.hi]
         emb = torch.empty(len(premises), self.embedding_size, dtype=self.dtype, device=self.device)
         if len(premises):
@@ -230,14 +293,26 @@ class B200PremiseRetriever:
         if words.shape[1] == 0:     # a rank without rows still takes part in the collective
             words = np.zeros((len(ctxs), 1), dtype=np.uint32)
         mask = torch.from_numpy(words.view(np.int32)).to(context_emb.device)
-        scores, idx, counts, _ = index.topk(context_emb, k, access_mask=mask, group=group, **ops)
+        scores, idx, counts, _ = index.topk(context_emb, k, access_mask=mask, **ops)
         if any(c < k for c in counts.cpu().tolist()):
             raise ValueError
         idx_h, scores_h = idx.cpu().tolist(), scores.cpu().tolist()
         return [[self.corpus.all_premises[i] for i in row] for row in idx_h], scores_h
 
     # ------------------------------------------------------------------ index I/O (reference retrieval/index.py:37-40)
-    def save_index(self, path: str) -> None:
+    def save_index(self, path: str, reference_layout: bool = True) -> None:
+        """Write the indexed corpus (`retrieval/index.py:37-40`: `IndexedCorpus(corpus, fp32 CPU embeddings)`).
+
+        `reference_layout=True` (default): a pickle a STOCK reference checkout loads — classes
+        `common.IndexedCorpus / Corpus / File / Premise`, `lean_dojo.Pos`, a networkx transitive-closure
+        graph (`reprover_b200.compat.dump_reference_index`); `load_corpus` of this package reads it back
+        through the compat loader.  `False`: this package's own (leaner) classes."""
         assert self.corpus is not None and not self.embeddings_staled
+        emb = self.corpus_embeddings.to(torch.float32).cpu()
         with open(path, "wb") as fh:
-            pickle.dump(IndexedCorpus(self.corpus, self.corpus_embeddings.to(torch.float32).cpu()), fh)
+            if reference_layout:
+                from .compat import dump_reference_index
+
+                dump_reference_index(self.corpus, emb, fh)
+            else:
+                pickle.dump(IndexedCorpus(self.corpus, emb), fh)

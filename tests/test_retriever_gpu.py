@@ -136,9 +136,19 @@ def test_index_roundtrip_and_cli(setup, tmp_path, cuda_device):
     out = tmp_path / "index.pickle"
     index_cli.main(["--ckpt_path", str(setup["ckpt"]), "--corpus-path", str(setup["jsonl"]),
                     "--output-path", str(out), "--batch-size", "16", "--max-seq-len", str(MAX_LEN)])
-    indexed = pickle.loads(out.read_bytes())
+    # the CLI writes the reference's own layout (common.* / lean_dojo.Pos / networkx): readable by a stock
+    # checkout; here (no `common` module) it is read back through the compat loader
+    with pytest.raises((ModuleNotFoundError, AttributeError)):
+        pickle.loads(out.read_bytes())
+    from reprover_b200.compat import load_reference_index
+
+    indexed = load_reference_index(str(out))
     assert indexed.embeddings.dtype == torch.float32 and indexed.embeddings.device.type == "cpu"
     assert torch.equal(indexed.embeddings, setup["retr"].corpus_embeddings.float().cpu())
+    assert [p.full_name for p in indexed.corpus.all_premises] == [p.full_name for p in setup["retr"].corpus.all_premises]
+    native = tmp_path / "native.pickle"
+    setup["retr"].save_index(str(native), reference_layout=False)
+    assert torch.equal(pickle.loads(native.read_bytes()).embeddings, indexed.embeddings)
     r2 = B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device)
     r2.load_corpus(str(out))                                # pickled IndexedCorpus -> fresh index (model.py:81-85)
     assert not r2.embeddings_staled
@@ -148,12 +158,31 @@ def test_index_roundtrip_and_cli(setup, tmp_path, cuda_device):
     assert r2.corpus_embeddings.device.type == "cuda" and r2.corpus_embeddings.dtype == torch.bfloat16
 
 
-def test_fp32_embedding_dtype_option(setup, cuda_device):
-    r = B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=torch.float32)
+def test_dtype_policy_is_loud(setup, cuda_device, tmp_path):
+    """The engine computes in bf16 only: asking for an fp32 / fp16 MODEL (what `dtype` means in the
+    reference, retrieval/model.py:52-66) is refused, not silently down-cast; fp32 OUTPUT tensors are a
+    separate option, and retrieval then keeps the caller's fp32 index untouched."""
+    for bad in (torch.float32, torch.float16):
+        with pytest.raises(NotImplementedError, match="bf16"):
+            B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=bad)
+    r = B200PremiseRetriever(str(setup["ckpt"]), max_seq_len=MAX_LEN, device=cuda_device, output_dtype=torch.float32)
     e = r.encode_texts(["⊢ x = x"])
     assert e.dtype == torch.float32 and abs(float(e.norm()) - 1.0) < 1e-5
-    with pytest.raises(NotImplementedError):
-        B200PremiseRetriever.load_hf(str(setup["ckpt"]), MAX_LEN, cuda_device, dtype=torch.float16)
+    r.load_corpus(setup["retr"].corpus)
+    r.reindex_corpus(32)
+    assert r.corpus_embeddings.dtype == torch.float32
+    a = r.retrieve("⊢ p ∧ q", "Synth/F3.lean", "t", Pos(120, 0), 7)
+    b = setup["retr"].retrieve("⊢ p ∧ q", "Synth/F3.lean", "t", Pos(120, 0), 7)
+    assert r.corpus_embeddings.dtype == torch.float32          # the fp32 index the caller sees is not replaced
+    assert [p.full_name for p in a[0]] == [p.full_name for p in b[0]]
+    # what generation/model.py:224-226 does with a retriever: persist encoder + tokenizer next to a generator
+    out = tmp_path / "saved"
+    r.encoder.save_pretrained(str(out))
+    r.tokenizer.save_pretrained(str(out))
+    r2 = B200PremiseRetriever.load_hf(str(out), MAX_LEN, cuda_device)
+    assert torch.equal(r2.encode_texts(["⊢ x = x"]), setup["retr"].encode_texts(["⊢ x = x"]))
+    ids = r.tokenizer("ab", return_tensors="pt").input_ids.tolist()
+    assert ids == [[100, 101, 1]]
 
 
 def test_validation_and_predict_steps(setup):
