@@ -17,9 +17,10 @@
 //   * per-query candidate heap in registers, one (score, index) key per lane, kept by warp shuffles
 //     (REDUX min + ballot); at the end each warp hands its 8 best to the CTA, the CTA its 16 best to
 //     global memory — 2368 keys per query instead of N scores;
-//   * the LAST CTA to finish (ticket counter) runs the tail: selects the n_res best keys, re-scores them
-//     in fp64 in the canonical order, ranks them under (score desc, index asc), writes the k results
-//     and runs the exactness guard (rpx_topk_common.cuh) against everything the heaps dropped.
+//   * every CTA re-scores its 16 rows in fp64 in the canonical order (one warp per row, all SMs in
+//     parallel) before it leaves; the LAST CTA to finish (ticket counter) runs the tail on those exact
+//     scores: selects the k best, ranks them under (score desc, index asc), writes the results and runs
+//     the exactness guard (rpx_topk_common.cuh) against everything the fp32 heaps dropped.
 // No sampling pass, no memsets, no second launch (the exact-path kernel that follows returns at once
 // unless the guard flagged a query).
 #include "rpx_common.cuh"
@@ -37,6 +38,11 @@ constexpr int kSqCtaKeep = 16;    // keys a CTA hands to the tail
 constexpr int kSqSelMax = 288;    // >= n_res + selection slack for k <= 200
 constexpr int kSqSelSlack = 16;
 
+struct SqCand {
+  uint64_t key64;  // dkey(fp64 score); 0 = empty slot
+  uint64_t idx;    // local row
+};
+
 struct SmallQParams {
   const __nv_bfloat16* Q;
   const __nv_bfloat16* E;
@@ -51,7 +57,7 @@ struct SmallQParams {
   int64_t* out_packed;
   int64_t idx_offset;
   GuardOut guard;
-  uint64_t* cta_keys;  // [grid][NQ][kSqCtaKeep]
+  SqCand* cta_cand;    // [grid][NQ][kSqCtaKeep] exact (fp64 score, row) of each CTA's best rows
   uint64_t* cta_thr;   // [grid][NQ] best key that CTA dropped (0: none)
   float guard_coeff;
   int q_base;          // number of the first query of this launch within the call (guard records)
@@ -187,8 +193,25 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
     else if (rank == kSqCtaKeep) atomicMax(reinterpret_cast<unsigned long long*>(&cdrop[q]), (unsigned long long)mine);
   }
   __syncthreads();
-  for (int t = tid; t < NQ * kSqCtaKeep; t += kSqThreads)
-    p.cta_keys[(size_t)blockIdx.x * NQ * kSqCtaKeep + t] = ckeys[t];
+  // ---- every CTA re-scores ITS candidates in fp64 (canonical order), one warp per row: 148 CTAs x 16 rows
+  // in parallel, while the rows are still warm — the tail then ranks exact scores and never touches the index
+  float err = 0.f;
+  for (int t = warp; t < NQ * kSqCtaKeep; t += kSqWarps) {
+    const int q = t / kSqCtaKeep;
+    const uint64_t key = ckeys[t];
+    SqCand c;
+    c.key64 = 0ull;
+    c.idx = ~0ull;
+    if (key != 0ull) {
+      const uint32_t row = ckey_idx(key);
+      const double s = dot64_canonical(reinterpret_cast<const __nv_bfloat16*>(sQ + (size_t)q * CH), p.E + (size_t)row * d, d, lane);
+      c.key64 = dkey(s);
+      c.idx = row;
+      err = fmaxf(err, fabsf((float)(s - (double)ckey_score(key))));
+    }
+    if (lane == 0) p.cta_cand[(size_t)blockIdx.x * NQ * kSqCtaKeep + t] = c;
+  }
+  if (lane == 0 && err > 0.f) atomicMax(&p.guard.state->max_err_bits, __float_as_uint(err));
   if (tid < NQ) p.cta_thr[(size_t)blockIdx.x * NQ + tid] = cdrop[tid];
   __threadfence();
   __syncthreads();
@@ -202,11 +225,12 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
   __threadfence();
 
   // ------------------------------------------------------------------ tail (last CTA only)
-  const int G = (int)gridDim.x * kSqCtaKeep;  // keys per query
-  uint64_t* keys = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tail_smem) + 15) & ~(uintptr_t)15);  // [G]
-  double* sel_score = reinterpret_cast<double*>(keys + G);        // [kSqSelMax]
-  uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_score + kSqSelMax);
-  float* sel_s32 = reinterpret_cast<float*>(sel_idx + kSqSelMax);
+  // exact (fp64 score, index) pairs of every CTA's candidates: select the k best, rank, write, guard
+  const int G = (int)gridDim.x * kSqCtaKeep;  // candidates per query
+  uint64_t* k64 = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tail_smem) + 15) & ~(uintptr_t)15);  // [G]
+  uint32_t* ix = reinterpret_cast<uint32_t*>(k64 + G);                                                            // [G]
+  uint64_t* sel_key = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ix + G) + 15) & ~(uintptr_t)15);   // [kSqSelMax]
+  uint32_t* sel_idx = reinterpret_cast<uint32_t*>(sel_key + kSqSelMax);                                            // [kSqSelMax]
   __shared__ uint64_t red64[32];
   __shared__ float redf[32];
   __shared__ int redi[32];
@@ -216,13 +240,14 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
   __shared__ uint32_t kth_idx;
 
   for (int q = 0; q < NQ; ++q) {
-    // gather this query's keys from every CTA
     uint64_t kmin = ~0ull, kmax = 0ull, udrop = 0ull;
     int valid = 0;
     for (int i = tid; i < G; i += kSqThreads) {
       const int cta = i / kSqCtaKeep, s = i - cta * kSqCtaKeep;
-      const uint64_t key = __ldcg(&p.cta_keys[((size_t)cta * NQ + q) * kSqCtaKeep + s]);
-      keys[i] = key;
+      const SqCand* src = &p.cta_cand[((size_t)cta * NQ + q) * kSqCtaKeep + s];
+      const uint64_t key = __ldcg(&src->key64);
+      k64[i] = key;
+      ix[i] = (uint32_t)__ldcg(&src->idx);
       if (key != 0ull) {
         ++valid;
         kmin = key < kmin ? key : kmin;
@@ -239,17 +264,18 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
     kmax = block_reduce<uint64_t>(kmax, red64, [](uint64_t a, uint64_t b) { return a > b ? a : b; }, 0ull);
     udrop = block_reduce<uint64_t>(udrop, red64, [](uint64_t a, uint64_t b) { return a > b ? a : b; }, 0ull);
     const int total = block_reduce<int>(valid, redi, [](int a, int b) { return a + b; }, 0);
-    // threshold: count(key >= lo) in [n_res, n_res + slack] (keys are distinct; empty slots are 0 < lo)
+    const int k = p.k;
+    // threshold on the fp64 keys: count(key >= lo) in [k, k + slack] unless ties hold it higher
     uint64_t lo = total > 0 ? kmin : 1ull;
-    if (total > p.n_res + kSqSelSlack) {
-      uint64_t hi = kmax;
-      int count_lo = total;
-      for (int iter = 0; count_lo > p.n_res + kSqSelSlack && hi - lo > 1; ++iter) {
+    int count_lo = total;
+    if (total > k + kSqSelSlack) {
+      uint64_t hi = kmax;  // count(>= kmax) >= 1; the loop keeps count(>= lo) >= k
+      for (int iter = 0; count_lo > k + kSqSelSlack && hi - lo > 1; ++iter) {
         const uint64_t mid = lo + (hi - lo) / 2;
         int m = 0;
-        for (int i = tid; i < G; i += kSqThreads) m += keys[i] >= mid ? 1 : 0;
+        for (int i = tid; i < G; i += kSqThreads) m += k64[i] >= mid ? 1 : 0;
         m = block_count(m, cslots, iter);
-        if (m >= p.n_res) {
+        if (m >= k) {
           lo = mid;
           count_lo = m;
         } else {
@@ -257,45 +283,37 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
         }
       }
     }
+    // more exact ties at the k-th score than the ranking buffer holds: let the exact path do it
+    const bool overflow = count_lo > kSqSelMax;
     for (int i = tid; i < G; i += kSqThreads) {
-      const uint64_t key = keys[i];
+      const uint64_t key = k64[i];
       if (key != 0ull && key >= lo) {
         const int pos = atomicAdd(&n_sel, 1);
         if (pos < kSqSelMax) {
-          sel_idx[pos] = ckey_idx(key);
-          sel_s32[pos] = ckey_score(key);
+          sel_key[pos] = key;
+          sel_idx[pos] = ix[i];
         }
       }
     }
-    __syncthreads();
-    const int ns = n_sel < kSqSelMax ? n_sel : kSqSelMax;
-    // exact fp64 re-scoring, one warp per candidate
+    float q2 = 0.f;
     const __nv_bfloat16* sq = reinterpret_cast<const __nv_bfloat16*>(sQ + (size_t)q * CH);
-    float err = 0.f, q2 = 0.f;
-    for (int c = warp; c < ns; c += kSqWarps) {
-      const double s = dot64_canonical(sq, p.E + (size_t)sel_idx[c] * d, d, lane);
-      if (lane == 0) {
-        sel_score[c] = s;
-        err = fmaxf(err, fabsf((float)(s - (double)sel_s32[c])));
-      }
-    }
     for (int i = tid; i < d; i += kSqThreads) {
       const float v = __bfloat162float(sq[i]);
       q2 = fmaf(v, v, q2);
     }
-    err = block_reduce<float>(err, redf, [](float a, float b) { return fmaxf(a, b); }, 0.f);
-    q2 = block_reduce<float>(q2, redf, [](float a, float b) { return a + b; }, 0.f);
+    q2 = block_reduce<float>(q2, redf, [](float a, float b) { return a + b; }, 0.f);  // (also orders n_sel / sel_*)
+    const int ns = n_sel < kSqSelMax ? n_sel : kSqSelMax;
     // rank by counting under (score desc, index asc); ranks are a permutation
-    const int k = p.k;
     for (int c = tid; c < ns; c += kSqThreads) {
-      const double sc = sel_score[c];
+      const uint64_t kc = sel_key[c];
       const uint32_t ic = sel_idx[c];
       int rank = 0;
       for (int j = 0; j < ns; ++j) {
-        const double sj = sel_score[j];
-        rank += (sj > sc || (sj == sc && sel_idx[j] < ic)) ? 1 : 0;
+        const uint64_t kj = sel_key[j];
+        rank += (kj > kc || (kj == kc && sel_idx[j] < ic)) ? 1 : 0;
       }
       if (rank < k) {
+        const double sc = undkey(kc);
         const size_t o = (size_t)q * k + rank;
         p.out_scores[o] = (float)sc;
         if (p.out_scores64) p.out_scores64[o] = sc;
@@ -304,10 +322,10 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
           p.out_packed[2 * o] = __double_as_longlong(sc);
           p.out_packed[2 * o + 1] = (int64_t)ic + p.idx_offset;
         }
-      }
-      if (rank == k - 1) {
-        kth_score = sc;
-        kth_idx = ic;
+        if (rank == k - 1) {
+          kth_score = sc;
+          kth_idx = ic;
+        }
       }
     }
     const int nvalid = ns < k ? ns : k;
@@ -324,11 +342,11 @@ __global__ void __launch_bounds__(kSqThreads, 1) smallq_topk_kernel(const SmallQ
     __syncthreads();
     if (tid == 0) {
       if (p.out_count) p.out_count[q] = nvalid;
-      // everything outside the re-scored set: dropped by a warp / CTA heap (udrop) or not selected (lo)
-      float u = -INFINITY;
-      if (udrop != 0ull) u = ckey_score(udrop);
-      if (total > ns) u = fmaxf(u, ckey_score(lo));
-      guard_decide(p.guard, p.q_base + q, k, ns, kth_score, kth_idx, u, q2, p.guard_coeff, err);
+      // the candidates were ranked by their exact scores; what can still be missing is a row a warp or
+      // CTA heap dropped on its fp32 score (udrop = the best such key)
+      const float u = udrop != 0ull ? ckey_score(udrop) : -INFINITY;
+      guard_decide(p.guard, p.q_base + q, k, overflow ? 0 : ns, kth_score, kth_idx, overflow ? INFINITY : u, q2,
+                   p.guard_coeff, 0.f);
     }
     __syncthreads();
   }
@@ -338,8 +356,8 @@ size_t smallq_smem_bytes(int nq_t, int d, int grid) {
   const size_t CH = (size_t)d >> 3;
   size_t b = (size_t)nq_t * CH * 16;
   b += (size_t)nq_t * (kSqWarps * kSqWarpKeep + kSqCtaKeep + 1) * 8;
-  b += 16 + (size_t)grid * kSqCtaKeep * 8;                 // tail: keys
-  b += (size_t)kSqSelMax * (sizeof(double) + 4 + 4);        // tail: sel arrays
+  b += 16 + (size_t)grid * kSqCtaKeep * (8 + 4);           // tail: fp64 keys + rows
+  b += 16 + (size_t)kSqSelMax * (8 + 4);                    // tail: ranking buffer
   return b;
 }
 
@@ -370,7 +388,7 @@ int launch_its(const SmallQParams& p, int its, int grid, size_t smem, cudaStream
 bool smallq_supported(int nq, int k, int d) { return nq >= 1 && nq <= 4 && k >= 1 && k <= 200 && d % 8 == 0 && d <= 2048; }
 
 size_t smallq_workspace_bytes(int num_sms) {
-  return align_up((size_t)num_sms * 4 * kSqCtaKeep * 8, 256) + align_up((size_t)num_sms * 4 * 8, 256);
+  return align_up((size_t)num_sms * 4 * kSqCtaKeep * sizeof(SqCand), 256) + align_up((size_t)num_sms * 4 * 8, 256);
 }
 
 // nq in 1..4: the kernel is instantiated for 1, 2 and 4 queries; 3 queries run as 2 + 1.
@@ -403,8 +421,8 @@ int launch_smallq_topk(const TopkCall& c, void* ws, int n_res) {
     p.guard.state = c.state;
     p.guard.flagged = c.flagged;
     p.guard.bounds = c.bounds;
-    p.cta_keys = reinterpret_cast<uint64_t*>(base);
-    p.cta_thr = reinterpret_cast<uint64_t*>(base + align_up((size_t)grid * 4 * kSqCtaKeep * 8, 256));
+    p.cta_cand = reinterpret_cast<SqCand*>(base);
+    p.cta_thr = reinterpret_cast<uint64_t*>(base + align_up((size_t)grid * 4 * kSqCtaKeep * sizeof(SqCand), 256));
     p.guard_coeff = guard_coeff_stream(c.d);
     p.q_base = q0;
     const size_t smem = smallq_smem_bytes(nq_t, c.d, grid);

@@ -98,12 +98,20 @@ class B200PremiseRetriever:
                 from transformers import AutoTokenizer, ByT5Tokenizer
             except ImportError as exc:  # pragma: no cover
                 raise RuntimeError("`retriever.tokenizer` needs the `transformers` package") from exc
+            # The engine tokenises as ByT5 does (bytes + 3, EOS = 1), whatever files the checkpoint ships; use
+            # the checkpoint's own tokenizer files only when they exist and are ByT5's
+            tok = None
             try:
                 from .engine import resolve_checkpoint_dir
 
-                self._tokenizer = AutoTokenizer.from_pretrained(resolve_checkpoint_dir(self.model_name))
+                ckpt = resolve_checkpoint_dir(self.model_name)
+                if os.path.exists(os.path.join(ckpt, "tokenizer_config.json")):
+                    cand = AutoTokenizer.from_pretrained(ckpt)
+                    if isinstance(cand, ByT5Tokenizer):
+                        tok = cand
             except Exception:
-                self._tokenizer = ByT5Tokenizer()   # the checkpoint ships no tokenizer files: ByT5's is parameter-free
+                tok = None
+            self._tokenizer = tok if tok is not None else ByT5Tokenizer()
         return self._tokenizer
 
     def load_corpus(self, path_or_corpus: Union[str, Corpus]) -> None:

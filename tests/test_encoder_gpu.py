@@ -142,6 +142,30 @@ def test_long_sequences_and_max_len_2048(rpx_lib, cuda_device, tiny):
     assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
 
 
+def test_byt5_small_full_depth_at_max_seq_len_2048(rpx_lib, cuda_device, out_dir):
+    """The production indexing shape at FULL depth: 12-layer ByT5-small, max_seq_len = 2048
+    (retrieval/index.py:33, prover/evaluate.py:106), lengths around every tiling boundary of the long
+    path — 1023 / 1024 tokens (8 query tiles, 16 key steps), 2047 / 2048 tokens, and a 2500-byte
+    string truncated to 2047 bytes + EOS — against the HF fp32 oracle (tolerance of SURVEY 8c)."""
+    cfg = dict(synth.BYT5_SMALL)
+    sd = synth.random_t5_state_dict(cfg, seed=synth.SEED)
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    lens = [1022, 1023, 2046, 2500, 2047]          # bytes; + EOS -> 1023, 1024, 2047, 2048 (truncated), 2048 tokens
+    rng = np.random.default_rng(21)
+    strs = [bytes(rng.choice(synth._ALPHABET, size=n).tolist()) for n in lens]
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in strs])]).astype(np.int64)
+    data = np.frombuffer(b"".join(strs), dtype=np.uint8)
+    got = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)
+    want = oracle_embeddings(cfg, sd, data, offsets, 2048, batch_size=1)
+    max_abs, min_cos = compare_embeddings(got, want)
+    (out_dir / "encoder_full_depth_2048.json").write_text(json.dumps({"max_abs": max_abs, "min_cos": min_cos, "byte_lens": lens}))
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
+    # the truncated string equals its first 2047 bytes encoded on their own (truncation includes the EOS)
+    cut = eng.encode_bytes(np.frombuffer(strs[3][:2047], dtype=np.uint8), np.array([0, 2047], dtype=np.int64), 2048,
+                           out_dtype=torch.float32)
+    assert torch.equal(cut[0], got[3])
+
+
 def test_many_short_sequences_and_chunking(rpx_lib, cuda_device, tiny):
     """Hundreds of sequences split over several engine calls (token-budget chunking) == one call."""
     cfg, sd = tiny
