@@ -130,6 +130,14 @@ int rpx_encode_ids(rpx_encoder* enc, const int64_t* d_input_ids, const int64_t* 
                    int32_t batch, int32_t seq_len, void* d_out, int32_t out_dtype,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Latency path: encode calls with at most `max_tokens` packed tokens (0 = never, the default) run the
+ * layer GEMMs on narrow 1-CTA tiles (128 tokens x 64 columns) that spread a single proof state's work
+ * over ~20-110 SMs instead of the 256 x 256 pair tiles that are sized for re-indexing.  This is the
+ * shape of the reference's per-state call (`retrieve`, retrieval/model.py:348-357).  Results agree with
+ * the throughput path to fp32 rounding of the RMSNorm statistics (not bit for bit), so a caller that needs
+ * batch-invariant bits (re-indexing) leaves it off. */
+int rpx_encoder_set_latency_tokens(rpx_encoder* enc, int32_t max_tokens);
+
 /* T5 bidirectional relative-position bucket of `relative_position` = key - query
  * (HF modeling_t5.py:189-234).  Pure host function (no GPU needed); exported so the
  * CPU test-suite can pin the table the attention kernel uses against the HF code. */

@@ -140,7 +140,9 @@ extern "C" int32_t rpx_t5_relative_bucket(int32_t relative_position, int32_t num
 struct rpx_encoder {
   rpx_t5_config cfg;
   int inner = 0;
-  int n_parts = 0;  // RMSNorm partial sums per row: ceil(d_model / 256) * 2
+  int n_parts = 0;      // RMSNorm partial sums per row on the throughput path: one per 256-wide n-tile
+  int n_parts_lat = 0;  // ... on the latency path: one per 64-wide n-tile
+  int latency_tokens = 0;  // calls with at most this many packed tokens take the latency path (0: never)
   const float* emb = nullptr;
   const float* final_ln = nullptr;
   const float* bias_lut = nullptr;
@@ -249,8 +251,9 @@ Workspace carve(const rpx_encoder* e, uint8_t* base, int64_t T, int64_t S) {
   w.qkv = (__nv_bfloat16*)take(T * 3 * inner * 2);
   w.attn = (__nv_bfloat16*)take(T * inner * 2);
   w.ffn = (__nv_bfloat16*)take(T * F * 2);
-  w.ssA = (float*)take((size_t)e->n_parts * T * 4);
-  w.ssB = (float*)take((size_t)e->n_parts * T * 4);
+  const size_t parts = e->n_parts > e->n_parts_lat ? e->n_parts : e->n_parts_lat;
+  w.ssA = (float*)take(parts * T * 4);
+  w.ssB = (float*)take(parts * T * 4);
   w.total = off;
   return w;
 }
@@ -283,11 +286,64 @@ struct Prof {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Latency path: one proof state per call (`retrieve`, retrieval/model.py:348-357, encodes ONE context).
+// With T of a few hundred tokens the 256 x 256 pair tiles of the throughput path leave most of the GPU
+// idle (QKV: 5 tiles, O / FFN-down: 6 tiles on 74 pairs) and every GEMM is bound by the latency of
+// streaming its weights through a handful of SMs.  Here the same contraction core runs 1-CTA tiles of
+// 128 tokens x 64 (FFN-up: 64 or 128) output columns with an 8-deep (6-deep) operand ring: 18-112 CTAs
+// pull the layer's 36 MB of weights in parallel.  K is never split, so every output element is still
+// accumulated over k in the same order as on the throughput path.
+constexpr int kLatBlockN = 64;
+constexpr int kLatStages = 8;
+
+int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, int T, int S, int max_len,
+                          cudaStream_t st) {
+  const rpx_t5_config& c = e->cfg;
+  const int D = c.d_model, inner = e->inner, F = c.d_ff, P = e->n_parts_lat;
+  const float inv_d = 1.0f / (float)D;
+  {
+    Prof p(e, st, 1);
+    EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
+    RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatStages>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st)));
+  }
+  {
+    Prof p(e, st, 2);
+    RPX_TRY(launch_t5_attention(ws.qkv, ws.attn, ws.cu_tokens, e->bias_lut, T, S, max_len, c.num_heads, c.d_kv,
+                                c.rel_max_distance, st));
+  }
+  {
+    Prof p(e, st, 3);
+    EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
+    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+  }
+  {
+    Prof p(e, st, 4);
+    // hidden units per tile: 32 (64-column tiles, T <= 128: 112 CTAs) or 64 (128-column tiles: 56 x ceil(T/128))
+    if (T <= kBlockM) {
+      EpiGeGLUT<32>::Params ep{ws.ffn, F, RowScale{ws.ssB, P, T, inv_d, c.ln_eps}};
+      RPX_TRY((launch_gemm<64, EpiGeGLUT<32>, false, kLatStages, true>(ws.h16, D, w.wi, D, T, 2 * F, D, ep, st)));
+    } else {
+      EpiGeGLUT<64>::Params ep{ws.ffn, F, RowScale{ws.ssB, P, T, inv_d, c.ln_eps}};
+      RPX_TRY((launch_gemm<128, EpiGeGLUT<64>, false, 6, true>(ws.h16, D, w.wi, D, T, 2 * F, D, ep, st)));
+    }
+  }
+  {
+    Prof p(e, st, 5);
+    EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
+    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+  }
+  return RPX_OK;
+}
+
 // The forward pass proper.  ws.ids / ws.cu_tokens are already populated on `st`.
 int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void* d_out, int out_dtype,
             cudaStream_t st) {
   const rpx_t5_config& c = e->cfg;
-  const int D = c.d_model, inner = e->inner, F = c.d_ff, P = e->n_parts;
+  const int D = c.d_model, inner = e->inner, F = c.d_ff;
+  // the latency path needs d_ff in 128-unit blocks for its split-B tiles (validate_cfg) and narrow-tile n
+  const bool latency = T <= e->latency_tokens && D % 32 == 0 && (3 * inner) % 32 == 0;
+  const int P = latency ? e->n_parts_lat : e->n_parts;
   const float inv_d = 1.0f / (float)D;
   {
     Prof p(e, st, 0);
@@ -301,9 +357,14 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   };
   RPX_TRY(dump(0));
   ResidualMaps maps;
-  RPX_TRY(make_residual_maps(&maps, ws.h32, ws.h16, T, D));
+  if (!latency) RPX_TRY(make_residual_maps(&maps, ws.h32, ws.h16, T, D));
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& w = e->layers[l];
+    if (latency) {
+      RPX_TRY(forward_latency_layer(e, ws, w, T, S, max_len, st));
+      RPX_TRY(dump(l + 1));
+      continue;
+    }
     {
       Prof p(e, st, 1);
       EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
@@ -367,6 +428,7 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
   e->cfg = *cfg;
   e->inner = inner;
   e->n_parts = ceil_div(D, kBlockN) * (EpiResidual::kWarps / 4);
+  e->n_parts_lat = ceil_div(D, kLatBlockN) * (EpiResidual::kWarps / 4);
   auto fail = [&](int code) {
     delete e;
     return code;
@@ -519,6 +581,13 @@ int rpx_encode_ids(rpx_encoder* enc, const int64_t* d_input_ids, const int64_t* 
   RPX_CUDA_OK(cudaMemcpyAsync(&flag, ws.flag, 4, cudaMemcpyDeviceToHost, st));
   RPX_CUDA_OK(cudaStreamSynchronize(st));
   RPX_REQUIRE((flag & 2) == 0, RPX_ERR_INVALID, "input_ids contains ids outside [0, %d)", enc->cfg.vocab_size);
+  return RPX_OK;
+}
+
+int rpx_encoder_set_latency_tokens(rpx_encoder* enc, int32_t max_tokens) {
+  RPX_REQUIRE(enc, RPX_ERR_INVALID, "null encoder");
+  RPX_REQUIRE(max_tokens >= 0, RPX_ERR_INVALID, "rpx_encoder_set_latency_tokens: %d", max_tokens);
+  enc->latency_tokens = max_tokens;
   return RPX_OK;
 }
 

@@ -81,7 +81,12 @@ struct TileCtx {
 //                                                  still in flight, e.g. prefetching)
 //   __device__ void tile(const TileCtx&);     (all 128 epilogue threads, warp-converged)
 //   __device__ void finish();
-template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false>
+// SPLIT_B (the gated FFN up-projection on narrow tiles): the B tile is two boxes of BLOCK_N/2 rows — the
+// gate rows and the linear-branch rows of the same BLOCK_N/2 hidden units.  The packed weight interleaves
+// wi_0 / wi_1 in 128-row blocks (rows [256j, 256j+128) gate, [256j+128, 256j+256) linear, see
+// rpx_encoder.cu), so n-tile t (units u0 = t * BLOCK_N/2) takes rows 256 (u0/128) + u0 % 128 and the same + 128;
+// tmB must then be encoded with a box of BLOCK_N/2 rows.
+template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false, bool SPLIT_B = false>
 __global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int tiles_m, int tiles_n, int n_blk_stride, typename Epi::Params ep) {
@@ -148,6 +153,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM, kEvictLast);
             tma_load_2d_hint(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
                              n_blk * n_blk_stride * BLOCK_N, kEvictFirst);
+          } else if (SPLIT_B) {
+            constexpr int H = BLOCK_N / 2;
+            const int u0 = n_blk * H;
+            const int gate_row = (u0 / 128) * 256 + (u0 % 128);
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK, gate_row);
+            tma_load_2d(sB + stage * Cfg::kBBytes + H * kBlockK * 2, &tmB, &full[stage], kb * kBlockK, gate_row + 128);
           } else {
             tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
@@ -572,11 +584,12 @@ __device__ __forceinline__ float gelu_new(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-// Gated-GELU FFN up projection (K9): the B operand interleaves wi_0 / wi_1 in
-// 128-row blocks, so accumulator columns [0,128) are the gate and [128,256) the
-// linear branch of the same 128 hidden units.
-//   out[m, n_blk*128 + j] = bf16( gelu_new(acc[j]*rs) * (acc[128+j]*rs) )
-struct EpiGeGLU {
+// Gated-GELU FFN up projection (K9): accumulator columns [0, HALF) are the gate and [HALF, 2*HALF) the
+// linear branch of the same HALF hidden units (HALF = 128: the 256-wide tiles of the throughput path, whose B
+// operand interleaves wi_0 / wi_1 in 128-row blocks; HALF = 64 / 32: the SPLIT_B narrow tiles).
+//   out[m, n_blk*HALF + j] = bf16( gelu_new(acc[j]*rs) * (acc[HALF+j]*rs) )
+template <int HALF>
+struct EpiGeGLUT {
   struct Params {
     __nv_bfloat16* out;  // [M, N/2]
     int ldo;
@@ -585,19 +598,19 @@ struct EpiGeGLU {
   static constexpr size_t kSmemBytes = 0;
   static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
-  __device__ EpiGeGLU(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ EpiGeGLUT(const Params& p_, uint8_t*, int, int) : p(p_) {}
   __device__ void before_wait(const TileCtx&) {}
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
     const float rs = ok ? p.rs.get(m) : 0.f;
-    for (int c = 32 * t.part; c < 128; c += 32 * t.split) {
+    for (int c = 32 * t.part; c < HALF; c += 32 * t.split) {
       uint32_t g[32], u[32];
       tmem_ld_32x32(t.tmem + c, g);
-      tmem_ld_32x32(t.tmem + 128 + c, u);
+      tmem_ld_32x32(t.tmem + HALF + c, u);
       tmem_ld_wait();
       if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + t.n_blk * 128 + c);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + t.n_blk * HALF + c);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float r[8];
@@ -616,5 +629,6 @@ struct EpiGeGLU {
   }
   __device__ void finish() {}
 };
+using EpiGeGLU = EpiGeGLUT<128>;
 
 }  // namespace rpx

@@ -112,6 +112,7 @@ class T5EncoderEngine:
             raise NotImplementedError("only the gated-gelu T5 v1.1 / ByT5 feed-forward is implemented")
         self.hidden_size = int(config["d_model"])
         self.max_tokens_per_call = int(max_tokens_per_call)
+        self.latency_tokens = 0
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
         self._ws_shape = (0, 0)
@@ -287,6 +288,12 @@ class T5EncoderEngine:
                                                   self._out_dtype(out_dtype), ws.data_ptr(), ws.numel(),
                                                   _stream_ptr(self.device)))
         return out
+
+    def set_latency_tokens(self, max_tokens: int) -> None:
+        """Engine calls with at most `max_tokens` packed tokens take the latency path (narrow tiles: one
+        proof state spread over many SMs); 0 switches it off.  See `rpx_encoder_set_latency_tokens`."""
+        _native.check(self.lib.rpx_encoder_set_latency_tokens(self._handle, int(max_tokens)))
+        self.latency_tokens = int(max_tokens)
 
     # ------------------------------------------------------------------ debug / profiling
     def set_debug_hidden(self, n_tokens: Optional[int]) -> Optional[torch.Tensor]:

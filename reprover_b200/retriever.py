@@ -237,8 +237,23 @@ class B200PremiseRetriever:
         ctxs = [Context(f, t, Pos.from_any(p), s) for s, f, t, p in zip(states, file_names, theorem_full_names, theorem_poses)]
         if not isinstance(k, int) or k < 1:
             raise ValueError(f"k={k!r}: retrieve() needs a positive number of premises")
-        context_emb = self.encode_texts([c.serialize() for c in ctxs])
+        context_emb = self._encode_states([c.serialize() for c in ctxs])
         return self.corpus.get_nearest_premises(self.index_handle(), ctxs, context_emb, k)
+
+    # Proof states are encoded one (or a few) at a time: below this many packed tokens per engine call the
+    # encoder's latency path is used (narrow tiles; `rpx_encoder_set_latency_tokens`).  Re-indexing never
+    # takes it, so the index stays independent of how premises are batched.
+    state_latency_tokens = 768
+
+    def _encode_states(self, texts: Sequence[str]) -> torch.Tensor:
+        enc = self.encoder
+        if not hasattr(enc, "set_latency_tokens"):
+            return self.encode_texts(texts)
+        enc.set_latency_tokens(self.state_latency_tokens)
+        try:
+            return self.encode_texts(texts)
+        finally:
+            enc.set_latency_tokens(0)
 
     def index_handle(self):
         """The engine's handle on the similarity index: the bf16 device copy of `corpus_embeddings`
@@ -296,7 +311,7 @@ class B200PremiseRetriever:
         """`retrieve_batch` over the row-sharded index (`ops`: injectable compute steps, see dist.sharded_topk)."""
         index = self.reindex_corpus_sharded(group=group)
         ctxs = [Context(f, t, Pos.from_any(p), s) for s, f, t, p in zip(states, file_names, theorem_full_names, theorem_poses)]
-        context_emb = self.encode_texts([c.serialize() for c in ctxs]).to(torch.bfloat16)
+        context_emb = self._encode_states([c.serialize() for c in ctxs]).to(torch.bfloat16)
         words = np.stack([self.corpus.accessible_mask_words_range(c.path, c.theorem_pos, index.lo, index.hi) for c in ctxs])
         if words.shape[1] == 0:     # a rank without rows still takes part in the collective
             words = np.zeros((len(ctxs), 1), dtype=np.uint32)

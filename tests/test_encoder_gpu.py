@@ -166,6 +166,27 @@ def test_byt5_small_full_depth_at_max_seq_len_2048(rpx_lib, cuda_device, out_dir
     assert torch.equal(cut[0], got[3])
 
 
+@pytest.mark.parametrize("n_tok", [1, 17, 128, 129, 300, 700])
+def test_latency_path_matches_oracle_and_throughput_path(rpx_lib, cuda_device, n_tok):
+    """`rpx_encoder_set_latency_tokens`: the narrow-tile kernels used for one proof state per call
+    (retrieval/model.py:348-357) against the HF fp32 oracle and against the throughput tiles."""
+    cfg = dict(synth.BYT5_SMALL)
+    cfg["num_layers"] = 3
+    sd = synth.random_t5_state_dict(cfg, seed=5)
+    eng = T5EncoderEngine(cfg, sd, cuda_device)
+    data, offsets = synth.synth_states(2 if n_tok < 300 else 1, seed=n_tok, min_len=max(n_tok - 1, 3), max_len=max(n_tok - 1, 3))
+    a = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)
+    eng.set_latency_tokens(4096)
+    b = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)
+    eng.set_latency_tokens(0)
+    c = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)
+    assert torch.equal(a, c)
+    assert (a - b).abs().max().item() <= 2e-5 and torch.nn.functional.cosine_similarity(a, b, dim=1).min().item() >= 0.999999
+    want = oracle_embeddings(cfg, sd, data, offsets, 2048)
+    max_abs, min_cos = compare_embeddings(b, want)
+    assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
+
+
 def test_many_short_sequences_and_chunking(rpx_lib, cuda_device, tiny):
     """Hundreds of sequences split over several engine calls (token-budget chunking) == one call."""
     cfg, sd = tiny
