@@ -99,6 +99,8 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                        __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens,
                        const float* __restrict__ bias_lut, int n_heads, int R, int ld_out) {
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  pdl_wait();  // qkv comes from the preceding GEMM (cu_seqlens / bias_lut are older, but one wait covers all)
+  pdl_launch_dependents();
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;
   const int q0 = qt * kQT;
@@ -400,9 +402,8 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
     configured = dev.device;
   }
   dim3 grid((max_len + kQT - 1) / kQT, n_heads, n_seqs);
-  t5_attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tm_q, tm_kv, out, cu_seqlens, bias_lut, n_heads,
-                                                               max_distance, inner);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(t5_attention_tc_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_enabled(), tm_q, tm_kv, out,
+                         cu_seqlens, bias_lut, n_heads, max_distance, inner));
   return RPX_OK;
 }
 

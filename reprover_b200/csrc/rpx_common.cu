@@ -2,11 +2,21 @@
 #include "rpx_common.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 
 namespace rpx {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RPX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 static thread_local char g_err[1024] = "";
 

@@ -25,6 +25,8 @@ __device__ __forceinline__ int find_seq(const int32_t* __restrict__ cu, int n, i
 __global__ void tokenize_bytes_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ cu_bytes,
                                       const int32_t* __restrict__ cu_tokens, int32_t* __restrict__ ids,
                                       int n_seqs, int n_tokens) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tokens) return;
   const int s = find_seq(cu_tokens, n_seqs, t);
@@ -78,6 +80,8 @@ __global__ void mask_lengths_kernel(const int64_t* __restrict__ mask, int32_t* _
 __global__ void embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ table,
                              float* __restrict__ h32, __nv_bfloat16* __restrict__ h16, float* __restrict__ ss,
                              int ss_stride, int n_parts, int n_tokens, int d_model) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= n_tokens) return;
@@ -103,6 +107,8 @@ __global__ void pool_normalize_kernel(const float* __restrict__ h32, const float
                                       int n_parts, const float* __restrict__ ln_w,
                                       const int32_t* __restrict__ cu_tokens, void* __restrict__ out,
                                       int out_dtype, int d_model, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int s = blockIdx.x;
   const int t0 = cu_tokens[s], t1 = cu_tokens[s + 1];
   const int i = threadIdx.x;
@@ -198,9 +204,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, const float* _
 
 int launch_tokenize_bytes(const uint8_t* bytes, const int64_t* cu_bytes, const int32_t* cu_tokens,
                           int32_t* ids, int n_seqs, int n_tokens, cudaStream_t stream) {
-  tokenize_bytes_kernel<<<ceil_div(n_tokens, 256), 256, 0, stream>>>(bytes, cu_bytes, cu_tokens, ids, n_seqs,
-                                                                     n_tokens);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(tokenize_bytes_kernel, dim3(ceil_div(n_tokens, 256)), dim3(256), 0, stream, pdl_enabled(), bytes,
+                         cu_bytes, cu_tokens, ids, n_seqs, n_tokens));
   return RPX_OK;
 }
 
@@ -222,9 +227,8 @@ int launch_mask_lengths(const int64_t* mask, int32_t* lens, int32_t* bad_flag, i
 int launch_embed(const int32_t* ids, const float* table, float* h32, __nv_bfloat16* h16, float* ss,
                  int ss_stride, int n_parts, int n_tokens, int d_model, cudaStream_t stream) {
   RPX_REQUIRE(d_model % 4 == 0, RPX_ERR_UNSUPPORTED, "embed: d_model must be a multiple of 4");
-  embed_kernel<<<ceil_div(n_tokens, 8), 256, 0, stream>>>(ids, table, h32, h16, ss, ss_stride, n_parts, n_tokens,
-                                                          d_model);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(embed_kernel, dim3(ceil_div(n_tokens, 8)), dim3(256), 0, stream, pdl_enabled(), ids, table, h32, h16,
+                         ss, ss_stride, n_parts, n_tokens, d_model));
   return RPX_OK;
 }
 
@@ -234,9 +238,8 @@ int launch_pool_normalize(const float* h32, const float* ss, int ss_stride, int 
   const int threads = (int)align_up((size_t)d_model / 4, 32);
   RPX_REQUIRE(d_model % 4 == 0 && threads <= 1024, RPX_ERR_UNSUPPORTED, "pool: unsupported d_model=%d", d_model);
   RPX_REQUIRE(out_dtype == RPX_DTYPE_BF16 || out_dtype == RPX_DTYPE_F32, RPX_ERR_INVALID, "pool: bad out dtype");
-  pool_normalize_kernel<<<n_seqs, threads, 0, stream>>>(h32, ss, ss_stride, n_parts, ln_w, cu_tokens, out,
-                                                        out_dtype, d_model, eps);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(pool_normalize_kernel, dim3(n_seqs), dim3(threads), 0, stream, pdl_enabled(), h32, ss, ss_stride,
+                         n_parts, ln_w, cu_tokens, out, out_dtype, d_model, eps));
   return RPX_OK;
 }
 

@@ -132,38 +132,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above touched only this CTA's shared memory / TMEM.  Under programmatic dependent launch
+  // (rpx_ptx.cuh) the preceding kernel may still be running: the A operand and whatever the epilogue reads
+  // from global memory are its outputs and must wait for it (pdl_wait), but the B operand — the weights —
+  // is never written by a kernel of the chain, so the producer streams the first ring's worth of B tiles
+  // BEFORE it waits: by the time the predecessor retires, a third of this CTA's weights are already on chip.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre = 0;  // stages of the first tile whose barrier is armed and whose B tile is already in flight
+      auto load_b = [&](int st, int n_blk, int kb) {
+        if (M_FASTEST) {
+          tma_load_2d_hint(sB + st * Cfg::kBBytes, &tmB, &full[st], kb * kBlockK, n_blk * n_blk_stride * BLOCK_N, kEvictFirst);
+        } else if (SPLIT_B) {
+          constexpr int H = BLOCK_N / 2;
+          const int u0 = n_blk * H;
+          const int gate_row = (u0 / 128) * 256 + (u0 % 128);
+          tma_load_2d(sB + st * Cfg::kBBytes, &tmB, &full[st], kb * kBlockK, gate_row);
+          tma_load_2d(sB + st * Cfg::kBBytes + H * kBlockK * 2, &tmB, &full[st], kb * kBlockK, gate_row + 128);
+        } else {
+          tma_load_2d(sB + st * Cfg::kBBytes, &tmB, &full[st], kb * kBlockK, n_blk * n_blk_stride * BLOCK_N);
+        }
+      };
+      if (!M_FASTEST && (int)blockIdx.x < num_tiles) {
+        const int n_blk0 = (int)blockIdx.x % tiles_n;
+        pre = num_kb < STAGES ? num_kb : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {  // fresh barriers: every stage is free
+          mbar_arrive_expect_tx(&full[kb], Cfg::kStageBytes);
+          load_b(kb, n_blk0, kb);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1, 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (pre > 0) {
+            --pre;  // armed, B in flight: only the A tile is missing
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            load_b(stage, n_blk, kb);
+          }
+          // L2 eviction hints: streamed operand evict-first, re-used operand evict-last.  Measured
+          // on B200 (A/B, one box): -20 % time for the similarity kernel (corpus streamed once, query
+          // block re-read by every tile), +3 % for the encoder GEMMs -> M_FASTEST only.  (An L2
+          // prefetch of the streamed operand a few k-blocks ahead of its TMA load was also measured:
+          // 6-12 % slower at every distance tried, removed.)
           if (M_FASTEST) {
-            // L2 eviction hints: streamed operand evict-first, re-used operand evict-last.  Measured
-            // on B200 (A/B, one box): -20 % time for the similarity kernel (corpus streamed once, query
-            // block re-read by every tile), +3 % for the encoder GEMMs -> M_FASTEST only.  (An L2
-            // prefetch of the streamed operand a few k-blocks ahead of its TMA load was also measured:
-            // 6-12 % slower at every distance tried, removed.)
             tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM, kEvictLast);
-            tma_load_2d_hint(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
-                             n_blk * n_blk_stride * BLOCK_N, kEvictFirst);
-          } else if (SPLIT_B) {
-            constexpr int H = BLOCK_N / 2;
-            const int u0 = n_blk * H;
-            const int gate_row = (u0 / 128) * 256 + (u0 % 128);
-            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK, gate_row);
-            tma_load_2d(sB + stage * Cfg::kBBytes + H * kBlockK * 2, &tmB, &full[stage], kb * kBlockK, gate_row + 128);
           } else {
             tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * kBlockK,
-                        n_blk * n_blk_stride * BLOCK_N);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -214,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane_grp = warp & 3;                            // TMEM lane group this warp may read
     const int row = lane_grp * 32 + (threadIdx.x & 31);       // row of the tile this thread owns
     const int part = (warp - kEpiWarp0) >> 2;                 // which share of the columns (0 when 4 warps)
+    pdl_wait();  // the epilogue reads (row scales, residual stream) and overwrites the predecessor's outputs
     Epi epi(ep, smem_extra, row, part);
     int as = 0;
     uint32_t aphase = 0;

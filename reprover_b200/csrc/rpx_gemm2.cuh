@@ -197,6 +197,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();  // peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // (see gemm_tc_kernel)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)

@@ -39,8 +39,8 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
   int grid = tiles_m * tiles_n;
   int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
   if (grid > cap) grid = cap;
-  kern<<<grid, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, 1, ep);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(gemm_threads<Epi>()), smem, stream, pdl_enabled(), tmA, tmB, M, N, K, tiles_m,
+                         tiles_n, 1, ep));
   return RPX_OK;
 }
 
@@ -73,8 +73,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, 
   }
   int pairs = tiles_m * tiles_n;
   if (pairs > dev.num_sms / 2) pairs = dev.num_sms / 2;
-  kern<<<2 * pairs, gemm_threads<Epi>(), smem, stream>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, ep);
-  RPX_CUDA_OK(cudaGetLastError());
+  RPX_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(gemm_threads<Epi>()), smem, stream, pdl_enabled(), tmA, tmB, M, N, K,
+                         tiles_m, tiles_n, ep));
   return RPX_OK;
 }
 

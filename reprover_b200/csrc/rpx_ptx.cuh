@@ -249,6 +249,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Kernels of one encoder call are launched with programmatic stream serialization (rpx_common.cuh
+// launch_pdl): a kernel may start while its predecessor in the stream is still running, so that its
+// prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible: every kernel
+// calls it before the first access to global memory another kernel wrote.  pdl_launch_dependents() lets
+// the successor be scheduled once every CTA of this grid has issued it.  Both are no-ops for a kernel
+// launched without the attribute.
+RPX_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+RPX_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- misc
 RPX_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
