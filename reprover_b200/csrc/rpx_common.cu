@@ -45,8 +45,52 @@ static PFN_cuTensorMapEncodeTiled_v12000 resolve_encode() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs a driver call per map; a single-state encode issues ~100 of them for the
+// same few dozen (pointer, shape) combinations call after call.  Small per-thread direct-mapped cache.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_cols, box_rows;
+  int elem, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows && elem == o.elem && swizzle == o.swizzle;
+  }
+};
+struct TmapSlot {
+  TmapKey key{};
+  bool valid = false;
+  alignas(64) CUtensorMap map;
+};
+constexpr int kTmapSlots = 512;
+thread_local TmapSlot g_tmaps[kTmapSlots];
+inline TmapSlot& tmap_slot(const TmapKey& k) {
+  uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.rows * 0xC2B2AE3D27D4EB4Full) ^ (k.cols << 17) ^ (k.ld << 29) ^ ((uint64_t)k.box_rows << 41) ^
+       ((uint64_t)k.box_cols << 49) ^ ((uint64_t)k.elem << 55) ^ ((uint64_t)k.swizzle << 58);
+  h ^= h >> 29;
+  return g_tmaps[h % kTmapSlots];
+}
+}  // namespace
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows) {
+  const TmapKey key{gptr, rows, cols, ld_elems, 64u, box_rows, 2, 128};
+  TmapSlot& slot = tmap_slot(key);
+  if (slot.valid && slot.key == key) {
+    *out = slot.map;
+    return RPX_OK;
+  }
+  RPX_TRY(make_tmap_bf16_2d_uncached(out, gptr, rows, cols, ld_elems, box_rows));
+  slot.key = key;
+  slot.map = *out;
+  slot.valid = true;
+  return RPX_OK;
+}
+
+int make_tmap_bf16_2d_uncached(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                               uint64_t ld_elems, uint32_t box_rows) {
   auto encode = resolve_encode();
   RPX_REQUIRE(encode != nullptr, RPX_ERR_CUDA, "cuTensorMapEncodeTiled not available from driver");
   RPX_REQUIRE((reinterpret_cast<uintptr_t>(gptr) & 15) == 0, RPX_ERR_INVALID,
@@ -68,6 +112,21 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 
 int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+  const TmapKey key{gptr, rows, cols, ld_elems, box_cols, box_rows, elem_bytes + 16, swizzle_bytes};
+  TmapSlot& slot = tmap_slot(key);
+  if (slot.valid && slot.key == key) {
+    *out = slot.map;
+    return RPX_OK;
+  }
+  RPX_TRY(make_tmap_2d_uncached(out, elem_bytes, gptr, rows, cols, ld_elems, box_cols, box_rows, swizzle_bytes));
+  slot.key = key;
+  slot.map = *out;
+  slot.valid = true;
+  return RPX_OK;
+}
+
+int make_tmap_2d_uncached(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   auto encode = resolve_encode();
   RPX_REQUIRE(encode != nullptr, RPX_ERR_CUDA, "cuTensorMapEncodeTiled not available from driver");
   RPX_REQUIRE(elem_bytes == 2 || elem_bytes == 4, RPX_ERR_INVALID, "TMA map: element size %d", elem_bytes);

@@ -46,11 +46,18 @@ const char* get_error();
 // Out-of-bounds box elements are zero-filled.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows);
+// (both map builders keep a small per-thread cache of encoded maps; the _uncached forms always call the driver)
+int make_tmap_bf16_2d_uncached(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                               uint64_t ld_elems, uint32_t box_rows);
 
 // General 2-D row-major map: `elem_bytes` 2 (bf16) or 4 (fp32), box {box_cols, box_rows}, swizzle span
 // `swizzle_bytes` in {0, 32, 64, 128} (box_cols * elem_bytes must not exceed it when non-zero).
 int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+int make_tmap_2d_uncached(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+int make_tmap_2d_uncached(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 struct DeviceInfo {
   int device = -1;

@@ -88,7 +88,7 @@ def test_retrieve_matches_reference_walk(setup):
         premises, scores = r.retrieve(state, path, "Synth.thm", pos, k)
         assert len(premises) == len(scores) == k
         ctx = Context(path, "Synth.thm", pos, state)
-        ctx_emb = r.encode_texts([state])
+        ctx_emb = r._encode_states([state])     # the (latency-path) encoding retrieve() itself uses
         want_p, want_s = ref.get_nearest_premises(corpus, r.corpus_embeddings.cpu(), [ctx], ctx_emb.cpu(), k)
         assert [p.full_name for p in premises] == [p.full_name for p in want_p[0]]
         assert np.allclose(scores, want_s[0], atol=1e-6)

@@ -1,5 +1,5 @@
 """One-sequence encode latency (device time, CUDA events) by token count: throughput tiles vs the latency path."""
-import json, sys
+import json, sys, time
 from pathlib import Path
 import numpy as np, torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -23,10 +23,13 @@ for T in (32, 64, 128, 200, 256, 384, 512, 768, 1024, 2048):
             eng.encode_packed_bytes(data, offs, 4096, o)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
+        t0 = time.perf_counter()
         for _ in range(20):
             eng.encode_packed_bytes(data, offs, 4096, o)
+        t1 = time.perf_counter()
         e1.record(); torch.cuda.synchronize()
         row[name] = e0.elapsed_time(e1) / 20
+        row[name + "_cpu_submit"] = (t1 - t0) / 20 * 1e3
         embs[name] = o.float().clone()
     row["max_abs_diff"] = float((embs["throughput"] - embs["latency"]).abs().max())
     out[T] = row
