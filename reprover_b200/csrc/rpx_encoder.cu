@@ -143,6 +143,7 @@ struct rpx_encoder {
   int n_parts = 0;      // RMSNorm partial sums per row on the throughput path: one per 256-wide n-tile
   int n_parts_lat = 0;  // ... on the latency path: one per 64-wide n-tile
   int latency_tokens = 0;  // calls with at most this many packed tokens take the latency path (0: never)
+  size_t layer_bytes = 0;  // packed weights of one layer (qkv | o | wi | wo, contiguous from LayerW::qkv)
   const float* emb = nullptr;
   const float* final_ln = nullptr;
   const float* bias_lut = nullptr;
@@ -297,15 +298,17 @@ struct Prof {
 constexpr int kLatBlockN = 64;
 constexpr int kLatStages = 8;
 
-int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, int T, int S, int max_len,
-                          cudaStream_t st) {
+int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, const void* next_weights,
+                          size_t next_bytes, int T, int S, int max_len, cudaStream_t st) {
   const rpx_t5_config& c = e->cfg;
   const int D = c.d_model, inner = e->inner, F = c.d_ff, P = e->n_parts_lat;
   const float inv_d = 1.0f / (float)D;
   {
     Prof p(e, st, 1);
     EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
-    RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatStages>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st)));
+    // the QKV projection occupies 18 x ceil(T/128) SMs: the rest of the GPU fetches the next layer's weights
+    RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatStages>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st, 0,
+                                                                       next_weights, next_bytes)));
   }
   {
     Prof p(e, st, 2);
@@ -361,7 +364,9 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& w = e->layers[l];
     if (latency) {
-      RPX_TRY(forward_latency_layer(e, ws, w, T, S, max_len, st));
+      const bool has_next = l + 1 < c.num_layers;
+      RPX_TRY(forward_latency_layer(e, ws, w, has_next ? e->layers[l + 1].qkv : nullptr, has_next ? e->layer_bytes : 0, T, S,
+                                    max_len, st));
       RPX_TRY(dump(l + 1));
       continue;
     }
@@ -480,6 +485,7 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
     TRY_E(launch_pack_weight(w->h_wi1[l], w->h_ln1[l], wi, F, D, 128, 128, 256, st));
     TRY_E(launch_pack_weight(w->h_wo[l], nullptr, wo, D, F, 0, D, D, st));
     e->layers[l] = LayerW{qkv, o, wi, wo};
+    e->layer_bytes = L.layer_stride;
   }
   // `buckets` is pageable host memory: make sure the H2D staging has finished before it dies.
   CUDA_E(cudaStreamSynchronize(st));

@@ -57,6 +57,14 @@ struct GemmCfg {
   }
 };
 
+// Kernel argument of gemm_tc_kernel: CTAs [0, work_ctas) run the GEMM (persistent over the tiles with that
+// stride); CTAs beyond prefetch `bytes` at `ptr` into L2 and leave.  work_ctas == gridDim.x: no helpers.
+struct L2Prefetch {
+  const void* ptr;
+  uint32_t bytes;
+  int work_ctas;
+};
+
 // What an epilogue functor sees for one output tile.
 struct TileCtx {
   uint32_t tmem;   // TMEM address of this thread's row, column 0 of the accumulator stage
@@ -89,8 +97,22 @@ struct TileCtx {
 template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false, bool SPLIT_B = false>
 __global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, int tiles_m, int tiles_n, int n_blk_stride, typename Epi::Params ep) {
+               int M, int N, int K, int tiles_m, int tiles_n, int n_blk_stride, typename Epi::Params ep,
+               L2Prefetch pf) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  if ((int)blockIdx.x >= pf.work_ctas) {
+    // Helper CTA (latency path): the GEMM itself keeps only a fraction of the SMs busy, so the launch is
+    // widened to the whole GPU and the surplus CTAs pull the NEXT layer's weights into L2 (36 MB of 126 MB)
+    // while this layer computes — its GEMMs then stream their B operand at L2 instead of DRAM latency.
+    pdl_launch_dependents();
+    const int n_help = (int)gridDim.x - pf.work_ctas;
+    const size_t lines = ((size_t)pf.bytes + 127) >> 7;
+    const char* base = static_cast<const char*>(pf.ptr);
+    for (size_t i = (size_t)((int)blockIdx.x - pf.work_ctas) * blockDim.x + threadIdx.x; i < lines;
+         i += (size_t)n_help * blockDim.x)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (i << 7)));
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tile bases.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -167,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       pdl_wait();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -202,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         int n_this = N - n_blk * n_blk_stride * BLOCK_N;
         if (n_this > BLOCK_N) n_this = BLOCK_N;
@@ -241,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Epi epi(ep, smem_extra, row, part);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
       TileCtx t;
       t.n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
       t.m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
@@ -257,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       t.N = N;
       t.tmem = tmem_base + as * BLOCK_N + ((uint32_t)(lane_grp * 32) << 16);
       {
-        const int nt = tile + gridDim.x;
+        const int nt = tile + pf.work_ctas;
         if (nt < num_tiles) {
           t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * kBlockM;
           t.next_n0 = (M_FASTEST ? nt / tiles_m : nt % tiles_n) * BLOCK_N;
