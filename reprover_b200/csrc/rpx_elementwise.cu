@@ -189,6 +189,101 @@ __global__ void pool_normalize_kernel(const float* __restrict__ h32, const float
   }
 }
 
+// Latency-path variant (one or a few sequences per call): the kernel above walks a sequence's tokens one
+// after the other in a single CTA — 56 dependent trips for a 225-token proof state, 0.13 ms, a quarter of the
+// whole single-state encode.  Here the 16 warps of the CTA take the tokens round-robin (lanes across the
+// row: 16-byte loads, 12 per lane per token, all in flight together), and the 16 partial rows are combined
+// in warp order.  (Not bit-identical to the sequential order above, like the rest of the latency path.)
+constexpr int kPoolWideWarps = 16;
+__global__ void __launch_bounds__(kPoolWideWarps * 32)
+pool_normalize_wide_kernel(const float* __restrict__ h32, const float* __restrict__ ss, int ss_stride, int n_parts,
+                           const float* __restrict__ ln_w, const int32_t* __restrict__ cu_tokens,
+                           void* __restrict__ out, int out_dtype, int d_model, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float part[];  // [kPoolWideWarps][d_model]
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const int t0 = cu_tokens[s], t1 = cu_tokens[s + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = d_model >> 2;
+  constexpr int kMaxIt = 16;  // d_model <= 16 * 32 * 4 = 2048 (checked by the launcher)
+  float4 acc[kMaxIt];
+#pragma unroll
+  for (int i = 0; i < kMaxIt; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_d = 1.0f / (float)d_model;
+  for (int t = t0 + warp; t < t1; t += kPoolWideWarps) {
+    float sum = 0.f;
+    for (int p = 0; p < n_parts; ++p) sum += ss[(int64_t)p * ss_stride + t];
+    const float rs = rsqrtf(sum * inv_d + eps);
+    const float4* row = reinterpret_cast<const float4*>(h32 + (int64_t)t * d_model);
+#pragma unroll
+    for (int g = 0; g < kMaxIt; g += 4) {  // four 16-byte loads per lane in flight
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * (g + j);
+        v[j] = c < n4 ? row[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[g + j].x = fmaf(v[j].x, rs, acc[g + j].x);
+        acc[g + j].y = fmaf(v[j].y, rs, acc[g + j].y);
+        acc[g + j].z = fmaf(v[j].z, rs, acc[g + j].z);
+        acc[g + j].w = fmaf(v[j].w, rs, acc[g + j].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxIt; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n4) reinterpret_cast<float4*>(part + (size_t)warp * d_model)[c] = acc[i];
+  }
+  __syncthreads();
+  const int i = threadIdx.x;
+  const bool active = i < n4;
+  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sq = 0.f;
+  if (active) {
+    for (int w = 0; w < kPoolWideWarps; ++w) {
+      const float4 a = reinterpret_cast<const float4*>(part + (size_t)w * d_model)[i];
+      tot.x += a.x;
+      tot.y += a.y;
+      tot.z += a.z;
+      tot.w += a.w;
+    }
+    const float inv_len = 1.0f / (float)(t1 - t0);
+    const float4 w4 = reinterpret_cast<const float4*>(ln_w)[i];
+    tot.x *= w4.x * inv_len;
+    tot.y *= w4.y * inv_len;
+    tot.z *= w4.z * inv_len;
+    tot.w *= w4.w * inv_len;
+    sq = tot.x * tot.x + tot.y * tot.y + tot.z * tot.z + tot.w * tot.w;
+  }
+  for (int off = 16; off; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  if (lane == 0) red[warp] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kPoolWideWarps ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float inv_norm = 1.0f / fmaxf(sqrtf(red[0]), 1e-12f);  // F.normalize: x / max(||x||_2, 1e-12)
+  if (active) {
+    tot.x *= inv_norm;
+    tot.y *= inv_norm;
+    tot.z *= inv_norm;
+    tot.w *= inv_norm;
+    if (out_dtype == RPX_DTYPE_F32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (int64_t)s * d_model)[i] = tot;
+    } else {
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (int64_t)s * d_model)[i] =
+          make_uint2(pack_bf16x2(tot.x, tot.y), pack_bf16x2(tot.z, tot.w));
+    }
+  }
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ src, const float* __restrict__ scale,
                                    __nv_bfloat16* __restrict__ dst, int n_rows, int n_cols, int dst_row0,
                                    int blk, int blk_stride) {
@@ -234,10 +329,21 @@ int launch_embed(const int32_t* ids, const float* table, float* h32, __nv_bfloat
 
 int launch_pool_normalize(const float* h32, const float* ss, int ss_stride, int n_parts, const float* ln_w,
                           const int32_t* cu_tokens, void* out, int out_dtype, int n_seqs, int d_model,
-                          float eps, cudaStream_t stream) {
+                          float eps, cudaStream_t stream, bool wide) {
   const int threads = (int)align_up((size_t)d_model / 4, 32);
   RPX_REQUIRE(d_model % 4 == 0 && threads <= 1024, RPX_ERR_UNSUPPORTED, "pool: unsupported d_model=%d", d_model);
   RPX_REQUIRE(out_dtype == RPX_DTYPE_BF16 || out_dtype == RPX_DTYPE_F32, RPX_ERR_INVALID, "pool: bad out dtype");
+  if (wide && d_model <= 2048 && d_model / 4 <= kPoolWideWarps * 32) {
+    const size_t smem = (size_t)kPoolWideWarps * d_model * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+      RPX_CUDA_OK(cudaFuncSetAttribute(pool_normalize_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
+    RPX_CUDA_OK(launch_pdl(pool_normalize_wide_kernel, dim3(n_seqs), dim3(kPoolWideWarps * 32), smem, stream, pdl_enabled(), h32,
+                           ss, ss_stride, n_parts, ln_w, cu_tokens, out, out_dtype, d_model, eps));
+    return RPX_OK;
+  }
   RPX_CUDA_OK(launch_pdl(pool_normalize_kernel, dim3(n_seqs), dim3(threads), 0, stream, pdl_enabled(), h32, ss, ss_stride,
                          n_parts, ln_w, cu_tokens, out, out_dtype, d_model, eps));
   return RPX_OK;

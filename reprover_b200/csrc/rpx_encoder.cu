@@ -398,7 +398,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   {
     Prof p(e, st, 6);
     RPX_TRY(launch_pool_normalize(ws.h32, ws.ssA, T, P, e->final_ln, ws.cu_tokens, d_out, out_dtype, S, D,
-                                  c.ln_eps, st));
+                                  c.ln_eps, st, latency));
   }
   return RPX_OK;
 }
