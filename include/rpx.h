@@ -231,6 +231,13 @@ int rpx_topk_merge_packed(const int64_t* d_packed, int32_t n_parts, int32_t nq, 
                           int32_t* d_out_count, void* stream);
 
 /* ------------------------------------------------------------------- test utilities
+ * Debug timeline: while `d_stamps` (device, n_slots x 8 uint64) is set, every launch of the 1-CTA GEMM
+ * kernel takes the next slot and its CTA 0 records %globaltimer at: kernel entry, prologue done,
+ * producer past the dependency wait, first operand stage landed, last MMA committed, accumulator seen by
+ * the epilogue, epilogue done, kernel exit.  NULL switches it off.  Not thread-safe; tooling only. */
+int rpx_debug_set_timeline(unsigned long long* d_stamps, int32_t n_slots);
+
+/*
  * Plain tcgen05 GEMM used by the parity tests of the contraction core:
  * C[M, N] (fp32, ldc = N) = A[M, K] * B[N, K]^T, bf16 inputs; K % 64 == 0, N % 32 == 0. */
 int rpx_gemm_bf16_f32(const void* d_A, const void* d_B, float* d_C, int32_t M, int32_t N,

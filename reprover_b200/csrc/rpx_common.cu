@@ -9,6 +9,13 @@
 
 namespace rpx {
 
+static unsigned long long* g_timeline = nullptr;
+static int g_timeline_slots = 0, g_timeline_next = 0;
+unsigned long long* next_timeline_slot() {
+  if (g_timeline == nullptr || g_timeline_next >= g_timeline_slots) return nullptr;
+  return g_timeline + 8 * (size_t)(g_timeline_next++);
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -186,6 +193,13 @@ extern "C" {
 
 const char* rpx_last_error(void) { return rpx::get_error(); }
 int rpx_version(void) { return RPX_VERSION; }
+
+int rpx_debug_set_timeline(unsigned long long* d_stamps, int32_t n_slots) {
+  rpx::g_timeline = d_stamps;
+  rpx::g_timeline_slots = d_stamps ? n_slots : 0;
+  rpx::g_timeline_next = 0;
+  return RPX_OK;
+}
 int rpx_device_check(void) {
   rpx::DeviceInfo d;
   return rpx::get_device_info(&d);

@@ -68,6 +68,9 @@ struct DeviceInfo {
 // Properties of the current device (cached per device ordinal).  Fails unless sm_100.
 int get_device_info(DeviceInfo* out);
 
+// Debug timeline (rpx_debug_set_timeline): each 1-CTA GEMM launch gets the next 8-stamp slot of the buffer.
+unsigned long long* next_timeline_slot();
+
 // RPX_PDL=0 switches programmatic dependent launch off (A/B measurements); default on.
 bool pdl_enabled();
 

@@ -63,7 +63,18 @@ struct L2Prefetch {
   const void* ptr;
   uint32_t bytes;
   int work_ctas;
+  unsigned long long* timeline;  // debug (rpx_debug_set_timeline): 8 %globaltimer stamps of CTA 0, or null
 };
+
+RPX_DEVICE unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RPX_STAMP(pf, i)                                                   \
+  do {                                                                     \
+    if ((pf).timeline != nullptr && blockIdx.x == 0) (pf).timeline[i] = global_ns(); \
+  } while (0)
 
 // What an epilogue functor sees for one output tile.
 struct TileCtx {
@@ -100,6 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int M, int N, int K, int tiles_m, int tiles_n, int n_blk_stride, typename Epi::Params ep,
                L2Prefetch pf) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  if (threadIdx.x == 0) RPX_STAMP(pf, 0);
   if ((int)blockIdx.x >= pf.work_ctas) {
     // Helper CTA (latency path): the GEMM itself keeps only a fraction of the SMs busy, so the launch is
     // widened to the whole GPU and the surplus CTAs pull the NEXT layer's weights into L2 (36 MB of 126 MB)
@@ -160,6 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // is never written by a kernel of the chain, so the producer streams the first ring's worth of B tiles
   // BEFORE it waits: by the time the predecessor retires, a third of this CTA's weights are already on chip.
   pdl_launch_dependents();
+  if (threadIdx.x == 0) RPX_STAMP(pf, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -189,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       pdl_wait();
+      RPX_STAMP(pf, 2);
       for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
@@ -235,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 3);
+          if (kb == 0 && tile == (int)blockIdx.x) RPX_STAMP(pf, 3);
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::kABytes));
           const uint64_t b_desc = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::kBBytes));
@@ -244,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
+          if (kb == num_kb - 1 && tile == (int)blockIdx.x) RPX_STAMP(pf, 4);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -292,8 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       epi.before_wait(t);
       mbar_wait(&tfull[as], aphase, 4);
+      if (threadIdx.x == 64 && tile == (int)blockIdx.x) RPX_STAMP(pf, 5);
       tc_fence_after();
       epi.tile(t);
+      if (threadIdx.x == 64 && tile == (int)blockIdx.x) RPX_STAMP(pf, 6);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       as ^= 1;
@@ -308,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 0) RPX_STAMP(pf, 7);
 }
 
 // ============================================================================ epilogues

@@ -40,7 +40,7 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
   int grid = tiles_m * tiles_n;
   int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
   if (grid > cap) grid = cap;
-  L2Prefetch pf{prefetch_ptr, (uint32_t)prefetch_bytes, grid};
+  L2Prefetch pf{prefetch_ptr, (uint32_t)prefetch_bytes, grid, next_timeline_slot()};
   if (prefetch_ptr != nullptr && prefetch_bytes > 0 && prefetch_bytes < ((size_t)1 << 32) && grid < dev.num_sms)
     grid = dev.num_sms;  // surplus SMs run prefetch helpers
   RPX_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(gemm_threads<Epi>()), smem, stream, pdl_enabled(), tmA, tmB, M, N, K, tiles_m,
