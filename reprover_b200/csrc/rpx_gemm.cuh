@@ -345,7 +345,17 @@ struct RowScale {
   __device__ float get(int m) const {
     if (ss_parts == nullptr) return 1.0f;
     float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += ss_parts[(size_t)p * part_stride + m];
+    // loads in batches of 8 (independent, all in flight together), additions in part order: the latency
+    // path has 23 parts per row and paid one L2 round trip per part with a plain loop
+    int p = 0;
+    for (; p + 8 <= n_parts; p += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ss_parts[(size_t)(p + j) * part_stride + m];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; p < n_parts; ++p) s += ss_parts[(size_t)p * part_stride + m];
     return rsqrtf(s * inv_dim + eps);
   }
 };
