@@ -263,6 +263,8 @@ class Corpus:
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop("_import_words_cache", None)  # derived data: keep index pickles lean
+        state.pop("_recent_masks", None)
+        state.pop("_recent_masks_dev", None)
         return state
 
     def __setstate__(self, state):
@@ -424,6 +426,13 @@ class Corpus:
         """`accessible_mask` packed little-endian into uint32 words (bit i&31 of word i>>5).
         Per query only the own-file prefix is recomputed; the imports part comes from a per-file cache."""
         pos = Pos.from_any(pos)
+        # proof search asks for the same (file, theorem position) over and over (one theorem, many states):
+        # keep the last few masks
+        recent = self.__dict__.setdefault("_recent_masks", {})
+        key = (path, pos.line_nb, pos.column_nb)
+        hit = recent.get(key)
+        if hit is not None and len(hit) == (len(self.all_premises) + 31) // 32:
+            return hit
         words = self._import_mask_words(path).copy()
         lo, hi = self._range[path]
         own = self.all_premises[lo:hi]
@@ -432,6 +441,9 @@ class Corpus:
             for i, p in enumerate(own, start=lo):
                 if p.full_name in visible_names:
                     words[i >> 5] |= np.uint32(1 << (i & 31))
+        if len(recent) >= 32:
+            recent.pop(next(iter(recent)))
+        recent[key] = words
         return words
 
     def accessible_mask_words_range(self, path: str, pos: Any, lo: int, hi: int) -> np.ndarray:

@@ -214,13 +214,52 @@ def nearest_premises_device(corpus, premise_embeddings: Union[torch.Tensor, Inde
     else:
         n_rows = e.n
     assert len(batch_context) == q.shape[0] and n_rows == len(corpus.all_premises)
-    words = np.stack([corpus.accessible_mask_words(ctx.path, ctx.theorem_pos) for ctx in batch_context])
-    mask = torch.from_numpy(words.view(np.int32)).to(dev)
+    mask = _device_mask(corpus, batch_context, dev)
     scores, idx, counts = sim_topk(q, e, k, access_mask=mask)
-    counts_h = counts.cpu().tolist()
-    if any(c < k for c in counts_h):
+    # one synchronisation for the three results (pinned staging, asynchronous copies)
+    nq = q.shape[0]
+    stage = _result_staging(nq, k)
+    stage[0][:nq].copy_(counts, non_blocking=True)
+    stage[1][:nq].copy_(idx, non_blocking=True)
+    stage[2][:nq].copy_(scores, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    if bool((stage[0][:nq] < k).any()):
         raise ValueError
-    idx_h = idx.cpu().tolist()
-    scores_h = scores.cpu().tolist()
-    results = [[corpus.all_premises[i] for i in row] for row in idx_h]
+    idx_h = stage[1][:nq].tolist()
+    scores_h = stage[2][:nq].tolist()
+    premises = corpus.all_premises
+    results = [[premises[i] for i in row] for row in idx_h]
     return results, scores_h
+
+
+_staging = {}
+
+
+def _result_staging(nq: int, k: int):
+    """Pinned host buffers for (counts, indices, scores) of up to nq queries, reused call after call."""
+    st = _staging.get(k)
+    if st is None or st[0].shape[0] < nq:
+        cap = max(nq, 8)
+        st = (torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, k, dtype=torch.int64).pin_memory(),
+              torch.empty(cap, k, dtype=torch.float32).pin_memory())
+        _staging[k] = st
+    return st
+
+
+def _device_mask(corpus, batch_context, dev: torch.device) -> torch.Tensor:
+    """[Q, words] int32 access bitmask on the device.  The rows of the last few (file, position) pairs stay
+    on the device: proof search retrieves for many states of one theorem, i.e. with the same mask."""
+    cache = corpus.__dict__.setdefault("_recent_masks_dev", {})
+    rows = []
+    for ctx in batch_context:
+        pos = ctx.theorem_pos
+        key = (ctx.path, pos.line_nb, pos.column_nb, dev.index)
+        words = corpus.accessible_mask_words(ctx.path, pos)
+        hit = cache.get(key)
+        if hit is None or hit[0] is not words:     # (the host array is the cache token: same object, same bits)
+            if len(cache) >= 32:
+                cache.pop(next(iter(cache)))
+            hit = (words, torch.from_numpy(words.view(np.int32)).to(dev))
+            cache[key] = hit
+        rows.append(hit[1])
+    return rows[0].unsqueeze(0) if len(rows) == 1 else torch.stack(rows)
