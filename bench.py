@@ -316,8 +316,9 @@ def run_engine(args) -> dict:
     }
     parity = (retrieve or {}).get("parity")
     if parity is not None and parity["mismatches"] != 0:
-        print(json.dumps(result), flush=True)
-        raise SystemExit(f"[bench] retrieve parity FAILED: {parity}")
+        exc = SystemExit(f"[bench] retrieve parity FAILED: {parity}")
+        exc.bench_result = result if rank == 0 else None
+        raise exc
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline_encode(cfg, sd, data, offsets, n_premises=args.cpu_sample)
     if world > 1:
@@ -637,9 +638,21 @@ def main():
     if args.impl == "engine" and args.warmup < 3:
         print(f"[bench] --warmup {args.warmup} raised to 3 (timing rules: at least 3 warm-up steps)", file=sys.stderr)
         args.warmup = 3
-    res = run_reference(args) if args.impl == "reference" else run_engine(args)
+    # stdout carries exactly ONE JSON line: anything a library prints to file descriptor 1 meanwhile
+    # (NCCL's version banner with NCCL_DEBUG=VERSION, for one) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        res = run_reference(args) if args.impl == "reference" else run_engine(args)
+    except SystemExit as exc:
+        res = getattr(exc, "bench_result", None)
+        if res is not None:
+            os.write(real_stdout, (json.dumps(res) + "\n").encode())
+        raise
     if res is not None:
-        print(json.dumps(res), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(res) + "\n").encode())
 
 
 if __name__ == "__main__":
