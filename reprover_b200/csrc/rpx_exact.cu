@@ -14,6 +14,8 @@
 //                       at once (~3 us), which is all the fast paths ever pay for it on ordinary data.
 //   row_norm_max_kernel HBM-bound pass over the index: max_i sum_j E[i,j]^2 -> IndexState::norm2_max
 //                       (the ||e|| factor of the guard's epsilon); runs once per rpx_index_create.
+#include <stdlib.h>
+
 #include "rpx_common.cuh"
 #include "rpx_kernels.cuh"
 #include "rpx_topk_common.cuh"
@@ -335,9 +337,19 @@ int launch_exact_topk(const TopkCall& c, void* cand_ws, bool all_queries) {
     configured = dev.device;
   }
   RPX_REQUIRE(smem <= 64 * 1024, RPX_ERR_UNSUPPORTED, "exact top-k: d=%d too wide", c.d);
-  void* args[] = {&p};
-  RPX_CUDA_OK(cudaLaunchCooperativeKernel((const void*)exact_topk_kernel, dim3(dev.num_sms), dim3(kExactThreads), args, smem,
-                                          c.st));
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("RPX_EXACT_COOP");  // experiment knob: 0 = plain launch (no co-residency guarantee)
+    coop = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (coop) {
+    void* args[] = {&p};
+    RPX_CUDA_OK(cudaLaunchCooperativeKernel((const void*)exact_topk_kernel, dim3(dev.num_sms), dim3(kExactThreads), args, smem,
+                                            c.st));
+  } else {
+    exact_topk_kernel<<<dev.num_sms, kExactThreads, smem, c.st>>>(p);
+    RPX_CUDA_OK(cudaGetLastError());
+  }
   return RPX_OK;
 }
 

@@ -559,48 +559,87 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
     }
   }
   __syncthreads();
-  const int ns = n_sel < kSelMax ? n_sel : kSelMax;
+  int ns = n_sel < kSelMax ? n_sel : kSelMax;
 
-  // ---- exact fp64 re-scoring, one warp per candidate
-  float err = 0.f, q2 = 0.f;
-  for (int c = warp; c < ns; c += kSelThreads / 32) {
-    const double s = dot64_canonical(sq, E + (size_t)sel_idx[c] * d, d, lane);
-    if (lane == 0) {
-      sel_score[c] = s;
-      err = fmaxf(err, fabsf((float)(s - (double)sel_s32[c])));
-    }
-  }
+  float q2 = 0.f;
   for (int i = tid; i < d; i += kSelThreads) {
     const float v = __bfloat162float(sq[i]);
     q2 = fmaf(v, v, q2);
   }
-  err = block_reduce<float>(err, redf, [](float a, float b) { return fmaxf(a, b); }, 0.f);
   q2 = block_reduce<float>(q2, redf, [](float a, float b) { return a + b; }, 0.f);
+  const float eps = guard_eps(o.guard, q2, o.guard_coeff);
 
-  // ---- rank by counting under (score desc, index asc); ranks are a permutation
-  for (int c = tid; c < ns; c += kSelThreads) {
-    const double sc = sel_score[c];
-    const uint32_t ic = sel_idx[c];
-    int rank = 0;
-    for (int j = 0; j < ns; ++j) {
-      const double sj = sel_score[j];
-      rank += (sj > sc || (sj == sc && sel_idx[j] < ic)) ? 1 : 0;
-    }
-    if (rank < k) {
-      const size_t oo = (size_t)q * k + rank;
-      o.scores[oo] = (float)sc;
-      if (o.scores64) o.scores64[oo] = sc;
-      o.idx[oo] = (int64_t)ic + o.idx_offset;
-      if (o.packed) {
-        o.packed[2 * oo] = __double_as_longlong(sc);
-        o.packed[2 * oo + 1] = (int64_t)ic + o.idx_offset;
+  // Two rounds at most.  Round 0 re-scores the n_res best by fp32 score.  If the guard cannot prove that
+  // set only because list entries just below the selection threshold might still belong (the common case
+  // on ordinary data: a handful of scores within epsilon of the k-th), round 1 takes in every list entry
+  // whose fp32 score is within 2 epsilon of the k-th exact score and ranks again — then everything left out
+  // is more than epsilon below the k-th.  Only what stage 1 itself dropped (tdrop) needs the exact path.
+  float err = 0.f;
+  float u = -INFINITY;
+  int first_new = 0;
+  bool proven = false;
+  for (int round = 0; round < 2; ++round) {
+    // ---- exact fp64 re-scoring of the candidates added this round, one warp per candidate
+    for (int c = first_new + warp; c < ns; c += kSelThreads / 32) {
+      const double s = dot64_canonical(sq, E + (size_t)sel_idx[c] * d, d, lane);
+      if (lane == 0) {
+        sel_score[c] = s;
+        err = fmaxf(err, fabsf((float)(s - (double)sel_s32[c])));
       }
     }
-    if (rank == k - 1) {
-      kth_score = sc;
-      kth_idx = ic;
+    __syncthreads();
+    // ---- rank by counting under (score desc, index asc); ranks are a permutation
+    for (int c = tid; c < ns; c += kSelThreads) {
+      const double sc = sel_score[c];
+      const uint32_t ic = sel_idx[c];
+      int rank = 0;
+      for (int j = 0; j < ns; ++j) {
+        const double sj = sel_score[j];
+        rank += (sj > sc || (sj == sc && sel_idx[j] < ic)) ? 1 : 0;
+      }
+      if (rank < k) {
+        const size_t oo = (size_t)q * k + rank;
+        o.scores[oo] = (float)sc;
+        if (o.scores64) o.scores64[oo] = sc;
+        o.idx[oo] = (int64_t)ic + o.idx_offset;
+        if (o.packed) {
+          o.packed[2 * oo] = __double_as_longlong(sc);
+          o.packed[2 * oo + 1] = (int64_t)ic + o.idx_offset;
+        }
+      }
+      if (rank == k - 1) {
+        kth_score = sc;
+        kth_idx = ic;
+      }
     }
+    __syncthreads();
+    u = tdrop;                                             // dropped by a stage-1 threshold / compaction
+    if (total > ns) u = fmaxf(u, ckey_score(lo));          // staged but not selected for re-scoring
+    proven = guard_proven(k, ns, kth_score, u, eps);
+    if (proven || round == 1 || ns < k || total <= ns) break;
+    // ---- widen: every staged entry with fp32 score >= kth - 2 eps joins the re-scored set
+    const float t_new = __double2float_rd(kth_score - 2.0 * (double)eps);
+    if (!(tdrop < t_new)) break;                           // stage 1 dropped rows that close: exact path
+    const uint64_t lo2 = (uint64_t)fkey(__float_as_uint(t_new)) << 32;
+    if (lo2 >= lo) break;                                  // (cannot happen: kth <= best unselected + eps)
+    int extra = 0;
+    for (int i = tid; i < total; i += kSelThreads) extra += (keys[i] >= lo2 && keys[i] < lo) ? 1 : 0;
+    extra = block_reduce<int>(extra, reinterpret_cast<int*>(redf), [](int a, int b) { return a + b; }, 0);
+    if (ns + extra > kSelMax) break;                       // too many near-ties for this buffer: exact path
+    first_new = ns;
+    for (int i = tid; i < total; i += kSelThreads) {
+      const uint64_t key = keys[i];
+      if (key >= lo2 && key < lo) {
+        const int pos = atomicAdd(&n_sel, 1);
+        sel_idx[pos] = ckey_idx(key);
+        sel_s32[pos] = ckey_score(key);
+      }
+    }
+    __syncthreads();
+    ns = n_sel;
+    lo = lo2;
   }
+
   const int valid = ns < k ? ns : k;
   for (int r = valid + tid; r < k; r += kSelThreads) {
     const size_t oo = (size_t)q * k + r;
@@ -612,12 +651,12 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
       o.packed[2 * oo + 1] = -1;
     }
   }
-  __syncthreads();
+  err = block_reduce<float>(err, redf, [](float a, float b) { return fmaxf(a, b); }, 0.f);
   if (tid == 0) {
     if (o.count) o.count[q] = valid;
-    float u = tdrop;                                      // dropped by a stage-1 threshold / compaction
-    if (total > ns) u = fmaxf(u, ckey_score(lo));          // staged but not selected for re-scoring
-    guard_decide(o.guard, o.q_base + q, k, ns, kth_score, kth_idx, u, q2, o.guard_coeff, err);
+    atomicMax(&o.guard.state->max_err_bits, __float_as_uint(err));
+    atomicMax(&o.guard.state->max_eps_bits, __float_as_uint(eps));
+    if (!proven) guard_flag(o.guard, o.q_base + q, k, ns, kth_score, kth_idx);
   }
 }
 

@@ -178,29 +178,39 @@ struct GuardOut {
   ExactBound* bounds;    // [nq]
 };
 
-// Called by ONE thread per query once the re-scored set has been ranked.
-//   n_ranked      number of re-scored candidates
-//   kth_score/idx the k-th best re-scored entry (valid when n_ranked >= k)
-//   u_bits        float bits of U, or 0xFF800000 (-inf) when nothing was left out
-//   q2            ||q||^2 (fp32)
-// Returns true when the result is proven.
+// The guard's epsilon for one query (also recorded in the diagnostics).
+__device__ __forceinline__ float guard_eps(const GuardOut& g, float q2, float coeff) {
+  return coeff * sqrtf(q2 * g.state->norm2_max) * 1.0001f;
+}
+
+// Is the ranked result proven?  n_ranked = number of re-scored candidates, kth_score = the k-th best of
+// them (valid when n_ranked >= k), u = the best fp32 score a row outside the re-scored set can have
+// (-inf: nothing was left out).
+__device__ __forceinline__ bool guard_proven(int k, int n_ranked, double kth_score, float u, float eps) {
+  const bool nothing_left_out = (u == -INFINITY);
+  if (n_ranked >= k) return nothing_left_out || kth_score > (double)u + (double)eps;
+  return nothing_left_out;
+}
+
+// Hands query q to the exact path (called by ONE thread).
+__device__ __forceinline__ void guard_flag(const GuardOut& g, int q, int k, int n_ranked, double kth_score,
+                                           uint32_t kth_idx) {
+  ExactBound b;
+  b.score = n_ranked >= k ? kth_score : -INFINITY;
+  b.idx = n_ranked >= k ? (int64_t)kth_idx : (int64_t)0x7FFFFFFF;
+  g.bounds[q] = b;
+  const uint32_t pos = atomicAdd(&g.state->n_flagged, 1u);
+  g.flagged[pos] = (uint32_t)q;
+}
+
+// Called by ONE thread per query once the re-scored set has been ranked.  Returns true when proven.
 __device__ __forceinline__ bool guard_decide(const GuardOut& g, int q, int k, int n_ranked, double kth_score,
                                              uint32_t kth_idx, float u, float q2, float coeff, float max_err) {
-  const float eps = coeff * sqrtf(q2 * g.state->norm2_max) * 1.0001f;
+  const float eps = guard_eps(g, q2, coeff);
   atomicMax(&g.state->max_err_bits, __float_as_uint(max_err));   // non-negative floats order like their bits
   atomicMax(&g.state->max_eps_bits, __float_as_uint(eps));
-  const bool nothing_left_out = (u == -INFINITY);
-  bool proven;
-  if (n_ranked >= k) proven = nothing_left_out || kth_score > (double)u + (double)eps;
-  else proven = nothing_left_out;
-  if (!proven) {
-    ExactBound b;
-    b.score = n_ranked >= k ? kth_score : -INFINITY;
-    b.idx = n_ranked >= k ? (int64_t)kth_idx : (int64_t)0x7FFFFFFF;
-    g.bounds[q] = b;
-    const uint32_t pos = atomicAdd(&g.state->n_flagged, 1u);
-    g.flagged[pos] = (uint32_t)q;
-  }
+  const bool proven = guard_proven(k, n_ranked, kth_score, u, eps);
+  if (!proven) guard_flag(g, q, k, n_ranked, kth_score, kth_idx);
   return proven;
 }
 

@@ -37,7 +37,35 @@ else:
     gathered = packed.unsqueeze(0).contiguous()
 out["merge"] = timed(lambda: topk_merge_packed(gathered))
 out["sharded_topk"] = timed(lambda: sharded_topk(Q, h, k, row_offset=rank * 200_000))
-if rank == 0:
-    print(json.dumps(out))
+# the same chain with events between the phases
+if world > 1:
+    reps = 30
+    acc = [0.0, 0.0, 0.0]
+    import time
+    for it in range(reps + 5):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        pk = sim_topk(Q, h, k, want_packed=True, idx_offset=rank * 200_000)[-1]
+        ev[1].record()
+        dist.all_gather_into_tensor(gathered.view(world * pk.shape[0], *pk.shape[1:]), pk)
+        ev[2].record()
+        topk_merge_packed(gathered)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= 5:
+            for j in range(3):
+                acc[j] += ev[j].elapsed_time(ev[j + 1])
+    out["chain_phases_synced_each_iter"] = [a / reps for a in acc]
+    t0 = time.perf_counter()
+    for _ in range(50):
+        pk = sim_topk(Q, h, k, want_packed=True, idx_offset=rank * 200_000)[-1]
+        dist.all_gather_into_tensor(gathered.view(world * pk.shape[0], *pk.shape[1:]), pk)
+        topk_merge_packed(gathered)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    out["chain_cpu_submit_ms"] = (t1 - t0) / 50 * 1e3
+    out["chain_wall_ms"] = (t2 - t0) / 50 * 1e3
+print(json.dumps({"rank": rank, **out}), flush=True)
 if world > 1:
     dist.destroy_process_group()
