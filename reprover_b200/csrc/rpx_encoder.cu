@@ -16,7 +16,6 @@
 // GEMM's B operand when the weights are packed, and the row scale rsqrt(mean(h^2)+eps)
 // is applied to the fp32 accumulator in that GEMM's epilogue (rpx_gemm.cuh RowScale).
 #include <math.h>
-#include <stdlib.h>
 
 #include <new>
 #include <vector>
@@ -107,10 +106,6 @@ int residual_gemm(const ResidualMaps& maps, const void* A, int64_t lda, const vo
   return encoder_gemm<EpiResidual>(A, lda, B, ldb, T, D, K, ep, st);
 }
 
-constexpr int kLatBlockN = 64;
-constexpr int kLatStages = 8;
-constexpr int kSplitKMaxItems = 160;  // split-K work items (tiles x splits) never exceed the SM count
-
 struct LayerW {
   const __nv_bfloat16* qkv;  // [3*inner, D]   (ln0 folded)
   const __nv_bfloat16* o;    // [D, inner]
@@ -149,7 +144,6 @@ struct rpx_encoder {
   int n_parts_lat = 0;  // ... on the latency path: one per 64-wide n-tile
   int latency_tokens = 0;  // calls with at most this many packed tokens take the latency path (0: never)
   size_t layer_bytes = 0;  // packed weights of one layer (qkv | o | wi | wo, contiguous from LayerW::qkv)
-  bool latency_splitk = true;  // RPX_LAT_SPLITK=0: A/B switch for the split-K down-projection
   const float* emb = nullptr;
   const float* final_ln = nullptr;
   const float* bias_lut = nullptr;
@@ -236,8 +230,6 @@ struct Workspace {
   __nv_bfloat16* ffn;
   float* ssA;
   float* ssB;
-  float* splitk;       // latency path: split-K partial tiles
-  uint32_t* tickets;   // latency path: split-K arrival counters (zero between launches)
   size_t total;
 };
 
@@ -263,8 +255,6 @@ Workspace carve(const rpx_encoder* e, uint8_t* base, int64_t T, int64_t S) {
   const size_t parts = e->n_parts > e->n_parts_lat ? e->n_parts : e->n_parts_lat;
   w.ssA = (float*)take(parts * T * 4);
   w.ssB = (float*)take(parts * T * 4);
-  w.splitk = (float*)take((size_t)kSplitKMaxItems * kBlockM * kLatBlockN * 4);
-  w.tickets = (uint32_t*)take((size_t)kSplitKMaxItems * 4);
   w.total = off;
   return w;
 }
@@ -305,6 +295,9 @@ struct Prof {
 // 128 tokens x 64 (FFN-up: 64 or 128) output columns with an 8-deep (6-deep) operand ring: 18-112 CTAs
 // pull the layer's 36 MB of weights in parallel.  K is never split, so every output element is still
 // accumulated over k in the same order as on the throughput path.
+constexpr int kLatBlockN = 64;
+constexpr int kLatStages = 8;
+
 int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, const void* next_weights,
                           size_t next_bytes, int T, int S, int max_len, cudaStream_t st) {
   const rpx_t5_config& c = e->cfg;
@@ -341,19 +334,7 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 5);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
-    // K = d_ff is long and there are only 23 x ceil(T/128) output tiles: a CTA is bound by what one SM can
-    // take in (~64 B/clk), so the k-blocks of a tile are spread over as many CTAs as there are idle SMs
-    DeviceInfo dev;
-    RPX_TRY(get_device_info(&dev));
-    const int tiles = ceil_div(T, kBlockM) * ceil_div(D, kLatBlockN);
-    const int num_kb = F / kBlockK;
-    int splits = dev.num_sms / tiles;
-    if (splits > 8) splits = 8;
-    if (splits * tiles > kSplitKMaxItems) splits = kSplitKMaxItems / tiles;
-    while (splits > 1 && (splits - 1) * ceil_div(num_kb, splits) >= num_kb) --splits;
-    if (splits < 1 || !e->latency_splitk) splits = 1;
-    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st, 0, nullptr, 0, splits,
-                                                                      ws.splitk, ws.tickets)));
+    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
   }
   return RPX_OK;
 }
@@ -367,10 +348,6 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   const bool latency = T <= e->latency_tokens && D % 32 == 0 && (3 * inner) % 32 == 0;
   const int P = latency ? e->n_parts_lat : e->n_parts;
   const float inv_d = 1.0f / (float)D;
-  struct PdlScope {
-    explicit PdlScope(bool on) { set_pdl_scope(on); }
-    ~PdlScope() { set_pdl_scope(false); }
-  } pdl_scope(latency);
   {
     Prof p(e, st, 0);
     RPX_TRY(launch_embed(ws.ids, e->emb, ws.h32, ws.h16, ws.ssA, T, P, T, D, st));
@@ -384,7 +361,6 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   RPX_TRY(dump(0));
   ResidualMaps maps;
   if (!latency) RPX_TRY(make_residual_maps(&maps, ws.h32, ws.h16, T, D));
-  if (latency) RPX_CUDA_OK(cudaMemsetAsync(ws.tickets, 0, (size_t)kSplitKMaxItems * 4, st));
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& w = e->layers[l];
     if (latency) {
@@ -458,10 +434,6 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
   e->inner = inner;
   e->n_parts = ceil_div(D, kBlockN) * (EpiResidual::kWarps / 4);
   e->n_parts_lat = ceil_div(D, kLatBlockN) * (EpiResidual::kWarps / 4);
-  {
-    const char* env = getenv("RPX_LAT_SPLITK");
-    e->latency_splitk = !(env && env[0] == '0');
-  }
   auto fail = [&](int code) {
     delete e;
     return code;

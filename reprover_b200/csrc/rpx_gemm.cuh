@@ -64,14 +64,6 @@ struct L2Prefetch {
   uint32_t bytes;
   int work_ctas;
   unsigned long long* timeline;  // debug (rpx_debug_set_timeline): 8 %globaltimer stamps of CTA 0, or null
-  // Split-K (latency path, K = 3584 on 23 x ceil(T/128) tiles): `splits` CTAs share one output tile, each
-  // contracting a contiguous slice of the k-blocks.  Every CTA parks its fp32 partial tile in `partials`
-  // ([tile][split][128][BLOCK_N]); the LAST one to arrive (ticket per tile, self-resetting) adds the partials
-  // in split order — a fixed order, whoever comes last — writes the sum back into its accumulator in TMEM
-  // and runs the ordinary epilogue.  splits == 1: none of this.
-  int splits;
-  float* partials;
-  uint32_t* tickets;
 };
 
 RPX_DEVICE unsigned long long global_ns() {
@@ -150,10 +142,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = K / kBlockK;
-  const int splits = pf.splits;
-  const int num_items = num_tiles * splits;             // work item = (tile, k-slice)
-  const int kb_per_split = (num_kb + splits - 1) / splits;
-  __shared__ int splitk_last;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -205,25 +193,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(sB + st * Cfg::kBBytes, &tmB, &full[st], kb * kBlockK, n_blk * n_blk_stride * BLOCK_N);
         }
       };
-      if (!M_FASTEST && (int)blockIdx.x < num_items) {
-        const int tile0 = (int)blockIdx.x / splits, kb00 = ((int)blockIdx.x % splits) * kb_per_split;
-        const int n_blk0 = tile0 % tiles_n;
-        const int n_kb0 = (kb00 + kb_per_split < num_kb ? kb00 + kb_per_split : num_kb) - kb00;
-        pre = n_kb0 < STAGES ? n_kb0 : STAGES;
-        for (int j = 0; j < pre; ++j) {  // fresh barriers: every stage is free
-          mbar_arrive_expect_tx(&full[j], Cfg::kStageBytes);
-          load_b(j, n_blk0, kb00 + j);
+      if (!M_FASTEST && (int)blockIdx.x < num_tiles) {
+        const int n_blk0 = (int)blockIdx.x % tiles_n;
+        pre = num_kb < STAGES ? num_kb : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {  // fresh barriers: every stage is free
+          mbar_arrive_expect_tx(&full[kb], Cfg::kStageBytes);
+          load_b(kb, n_blk0, kb);
         }
       }
       pdl_wait();
       RPX_STAMP(pf, 2);
-      for (int item = blockIdx.x; item < num_items; item += pf.work_ctas) {
-        const int tile = item / splits;
-        const int kb0 = (item % splits) * kb_per_split;
-        const int kb1 = kb0 + kb_per_split < num_kb ? kb0 + kb_per_split : num_kb;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         const int m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           if (pre > 0) {
             --pre;  // armed, B in flight: only the A tile is missing
           } else {
@@ -255,10 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int item = blockIdx.x; item < num_items; item += pf.work_ctas) {
-        const int tile = item / splits;
-        const int kb0 = (item % splits) * kb_per_split;
-        const int kb1 = kb0 + kb_per_split < num_kb ? kb0 + kb_per_split : num_kb;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
         const int n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
         int n_this = N - n_blk * n_blk_stride * BLOCK_N;
         if (n_this > BLOCK_N) n_this = BLOCK_N;
@@ -267,19 +247,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 3);
-          if (kb == kb0 && item == (int)blockIdx.x) RPX_STAMP(pf, 3);
+          if (kb == 0 && tile == (int)blockIdx.x) RPX_STAMP(pf, 3);
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::kABytes));
           const uint64_t b_desc = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (kb == kb1 - 1 && item == (int)blockIdx.x) RPX_STAMP(pf, 4);
+          if (kb == num_kb - 1 && tile == (int)blockIdx.x) RPX_STAMP(pf, 4);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -299,8 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Epi epi(ep, smem_extra, row, part);
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = blockIdx.x; item < num_items; item += pf.work_ctas) {
-      const int tile = item / splits;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
       TileCtx t;
       t.n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
       t.m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
@@ -316,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       t.N = N;
       t.tmem = tmem_base + as * BLOCK_N + ((uint32_t)(lane_grp * 32) << 16);
       {
-        const int nt = splits == 1 ? tile + pf.work_ctas : num_tiles;  // (no look-ahead across split-K items)
+        const int nt = tile + pf.work_ctas;
         if (nt < num_tiles) {
           t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * kBlockM;
           t.next_n0 = (M_FASTEST ? nt / tiles_m : nt % tiles_n) * BLOCK_N;
@@ -329,59 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       epi.before_wait(t);
       mbar_wait(&tfull[as], aphase, 4);
-      if (threadIdx.x == 64 && item == (int)blockIdx.x) RPX_STAMP(pf, 5);
+      if (threadIdx.x == 64 && tile == (int)blockIdx.x) RPX_STAMP(pf, 5);
       tc_fence_after();
-      bool run_epilogue = true;
-      if (splits > 1) {
-        // park this CTA's partial tile (thread = row: 128 contiguous bytes per 32-column chunk)
-        float* mine = pf.partials + ((size_t)item * kBlockM + row) * BLOCK_N;
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t.tmem + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            __stcg(reinterpret_cast<float4*>(mine + c + j),
-                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-        }
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * Epi::kWarps) : "memory");   // every row of the partial is out
-        if (threadIdx.x == 64) {
-          const uint32_t arrived = atomicAdd(&pf.tickets[tile], 1u);
-          splitk_last = (arrived == (uint32_t)splits - 1) ? 1 : 0;
-          if (splitk_last) pf.tickets[tile] = 0u;                              // ready for the next launch
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * Epi::kWarps) : "memory");
-        run_epilogue = splitk_last != 0;
-        if (run_epilogue) {
-          __threadfence();
-          // sum of the partials in split order -> back into this CTA's accumulator
-          const float* base = pf.partials + ((size_t)tile * splits * kBlockM + row) * BLOCK_N;
-          for (int c = 0; c < BLOCK_N; c += 32) {
-            float acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-            for (int sp = 0; sp < splits; ++sp) {
-              const float4* src = reinterpret_cast<const float4*>(base + (size_t)sp * kBlockM * BLOCK_N + c);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x = __ldcg(src + j);
-                acc[4 * j] += x.x;
-                acc[4 * j + 1] += x.y;
-                acc[4 * j + 2] += x.z;
-                acc[4 * j + 3] += x.w;
-              }
-            }
-            uint32_t v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
-            tmem_st_32x32(t.tmem + c, v);
-          }
-          tmem_st_wait();
-        }
-      }
-      if (run_epilogue) epi.tile(t);
-      if (threadIdx.x == 64 && item == (int)blockIdx.x) RPX_STAMP(pf, 6);
+      epi.tile(t);
+      if (threadIdx.x == 64 && tile == (int)blockIdx.x) RPX_STAMP(pf, 6);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       as ^= 1;

@@ -15,7 +15,7 @@ constexpr int kGemmStages = 4;
 template <int BLOCK_N, class Epi, bool M_FASTEST = false, int STAGES = kGemmStages, bool SPLIT_B = false>
 int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 const typename Epi::Params& ep, cudaStream_t stream, int grid_limit = 0, const void* prefetch_ptr = nullptr,
-                size_t prefetch_bytes = 0, int splits = 1, float* splitk_partials = nullptr, uint32_t* splitk_tickets = nullptr) {
+                size_t prefetch_bytes = 0) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
   RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
@@ -37,14 +37,10 @@ int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
     RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_dev = dev.device;
   }
-  RPX_REQUIRE(splits >= 1 && (splits == 1 || (splitk_partials && splitk_tickets && !M_FASTEST && Epi::kWarps == 4)),
-              RPX_ERR_INVALID, "gemm: bad split-K arguments");
-  RPX_REQUIRE(splits == 1 || (splits - 1) * ceil_div(K / kBlockK, splits) < K / kBlockK, RPX_ERR_INVALID,
-              "gemm: %d splits leave an empty k-slice (K = %d)", splits, K);
-  int grid = tiles_m * tiles_n * splits;
+  int grid = tiles_m * tiles_n;
   int cap = grid_limit > 0 ? grid_limit : dev.num_sms;
   if (grid > cap) grid = cap;
-  L2Prefetch pf{prefetch_ptr, (uint32_t)prefetch_bytes, grid, next_timeline_slot(), splits, splitk_partials, splitk_tickets};
+  L2Prefetch pf{prefetch_ptr, (uint32_t)prefetch_bytes, grid, next_timeline_slot()};
   if (prefetch_ptr != nullptr && prefetch_bytes > 0 && prefetch_bytes < ((size_t)1 << 32) && grid < dev.num_sms)
     grid = dev.num_sms;  // surplus SMs run prefetch helpers
   RPX_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(gemm_threads<Epi>()), smem, stream, pdl_enabled(), tmA, tmB, M, N, K, tiles_m,

@@ -809,7 +809,7 @@ int launch_sim_epi(const __nv_bfloat16* Q, int nq, const __nv_bfloat16* E, int64
   int64_t tiles = (int64_t)pl.tiles_m * tiles_n;
   const int grid = tiles < pl.grid ? (int)tiles : pl.grid;  // stays a multiple of tiles_m
   kern<<<grid, gemm_threads<Epi>(), smem, st>>>(tmA, tmB, pl.tiles_m * kBlockM, (int)n, d, pl.tiles_m, tiles_n, stride,
-                                                ep, L2Prefetch{nullptr, 0u, grid, nullptr, 1, nullptr, nullptr});
+                                                ep, L2Prefetch{nullptr, 0u, grid, nullptr});
   RPX_CUDA_OK(cudaGetLastError());
   return RPX_OK;
 }
