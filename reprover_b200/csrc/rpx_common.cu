@@ -16,13 +16,15 @@ unsigned long long* next_timeline_slot() {
   return g_timeline + 8 * (size_t)(g_timeline_next++);
 }
 
+static thread_local bool g_pdl_scope = false;
+void set_pdl_scope(bool on) { g_pdl_scope = on; }
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("RPX_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("RPX_PDL");  // 0: never; 2: every encoder launch; default: latency path only
+    v = e ? atoi(e) : 1;
   }
-  return v != 0;
+  return v == 2 || (v == 1 && g_pdl_scope);
 }
 
 static thread_local char g_err[1024] = "";

@@ -348,6 +348,10 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   const bool latency = T <= e->latency_tokens && D % 32 == 0 && (3 * inner) % 32 == 0;
   const int P = latency ? e->n_parts_lat : e->n_parts;
   const float inv_d = 1.0f / (float)D;
+  struct PdlScope {
+    explicit PdlScope(bool on) { set_pdl_scope(on); }
+    ~PdlScope() { set_pdl_scope(false); }
+  } pdl_scope(latency);
   {
     Prof p(e, st, 0);
     RPX_TRY(launch_embed(ws.ids, e->emb, ws.h32, ws.h16, ws.ssA, T, P, T, D, st));
