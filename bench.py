@@ -429,6 +429,11 @@ def retrieve_leg(Q, E, handle, k, rank, world, dev, peaks, e0, e1, K, W, check_p
                      "algorithmic_bytes": bytes_alg, "peak_source": peaks["source"],
                      "note": "whole retrieve (every launch of the call [+ all-gather + merge]) vs max(t_MMA, t_HBM) of one pass over the index"},
     }
+    if bound == "hbm" and nq <= 2:
+        tpath = ROOT / "profiles" / "roofline_traffic.json"
+        if tpath.exists():
+            leg["roofline"]["traffic"] = json.loads(tpath.read_text()).get("smallq_topk_dram_bytes_per_launch")
+            leg["roofline"]["kernel"] = "smallq_topk_kernel<1,6> (one streaming pass over the bf16 index, fused per-warp heaps + fp64 re-score + rank)"
     if check_parity:
         r = retrieve_dev()
         torch.cuda.synchronize()
