@@ -207,6 +207,8 @@ class T5EncoderEngine:
             return _native.RPX_DTYPE_F32
         raise ValueError(f"unsupported output dtype {dtype}")
 
+    MAX_SEQS_PER_CALL = 65535
+
     def token_counts(self, offsets: np.ndarray, max_seq_len: int) -> np.ndarray:
         """ByT5 token count of each string: bytes + EOS, truncated to max_seq_len."""
         return np.minimum(np.diff(offsets) + 1, max_seq_len)
@@ -243,7 +245,7 @@ class T5EncoderEngine:
         while lo < n:
             hi = int(np.searchsorted(cum, cum[lo] + self.max_tokens_per_call, side="right")) - 1
             hi = max(hi, lo + 1)
-            hi = min(hi, n)
+            hi = min(hi, n, lo + self.MAX_SEQS_PER_CALL)   # (the attention grid takes at most 65535 sequences)
             b0, b1 = int(offsets[lo]), int(offsets[hi])
             d_bytes = data_t[b0:b1].to(self.device, non_blocking=True) if b1 > b0 else torch.empty(
                 1, dtype=torch.uint8, device=self.device)
