@@ -438,7 +438,7 @@ sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_r
 // matters: Q = 1 0.192 vs 0.202 ms, Q = 64 0.166 vs 0.178 ms), 256 when there are enough queries to
 // fill the GPU (4 CTAs per SM instead of 2 overlap the staging / bisection / gather phases of different
 // queries: Q = 1024 0.607 vs 0.627 ms).
-constexpr int kSelThreadsLatency = 512, kSelThreadsThroughput = 256, kSelThroughputMinQueries = 512;
+constexpr int kSelThreadsLatency = 1024, kSelThreadsThroughput = 256, kSelThroughputMinQueries = 512;
 constexpr int kSelMax = 288;  // >= largest re-score set (k + margin + selection slack)
 
 __device__ __forceinline__ uint64_t ckey(uint2 e) { return ckey32(e.x, e.y); }
