@@ -380,11 +380,202 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-shot variant for short sequences (<= 256 keys) on the encoder's latency path: one proof
+// state is 2 query tiles x 6 heads = 12 CTAs, and with the streaming kernel above each of them walks 4
+// dependent key steps (S MMA -> softmax -> PV MMA, ~2.5 us each).  Here the whole key range is one step:
+// S[128 x 256] in TMEM from ONE group of N = 256 MMAs, a two-pass softmax straight out of TMEM (no running
+// maximum, no O rescale), P as four 128 x 64 K-major tiles, O from one run of PV MMAs.  One CTA per SM
+// (the accumulators take 320 of the 512 TMEM columns) — irrelevant at 12 CTAs.
+constexpr int kShortKeys = 256;
+constexpr int kShortOffQ = 0;
+constexpr int kShortOffK = kQBytes;                                  // [256 keys][64 bf16]
+constexpr int kShortOffV = kQBytes + kShortKeys * 128;
+constexpr int kShortOffP = kQBytes + 2 * kShortKeys * 128;           // 4 tiles of [128 rows][64 keys]
+constexpr int kShortOffBias = kShortOffP + 4 * kQBytes;
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                          __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens,
+                          const float* __restrict__ bias_lut, int n_heads, int R, int ld_out) {
+  const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int t0 = cu_seqlens[seq];
+  const int len = cu_seqlens[seq + 1] - t0;   // <= kShortKeys (checked by the launcher through max_len)
+  const int q0 = qt * kQT;
+  if (q0 >= len) return;  // whole CTA
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  float* sBias = reinterpret_cast<float*>(smem + kShortOffBias);
+  const int lut_w = 2 * R + 1;
+  const int bstride = bias_copy_stride(R);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kShortOffBias + 4 * bstride * 4);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = n_heads * kHD;
+  const int n_box = (len + kKT - 1) / kKT;            // 64-key TMA boxes of K and of V
+  const int n_mma = (len + 15) & ~15;                 // key extent of the MMAs
+
+  if (threadIdx.x < 128)
+    for (int i = threadIdx.x; i < 4 * bstride; i += 128) {
+      const int c = i / bstride, k = i - c * bstride;
+      sBias[i] = bias_lut[head * lut_w + min(max(k + c - 31, 0), 2 * R)];
+    }
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);  // S: columns [0, 256), O: [256, 320)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + kShortKeys;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
+      mbar_arrive_expect_tx(bar_q, kQBytes);
+      tma_load_2d(smem + kShortOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
+      mbar_arrive_expect_tx(bar_k, (uint32_t)(n_box * kKVBytes));
+      for (int b = 0; b < n_box; ++b) tma_load_2d(smem + kShortOffK + b * kKVBytes, &tm_kv, bar_k, kcol, t0 + b * kKT);
+      mbar_arrive_expect_tx(bar_v, (uint32_t)(n_box * kKVBytes));
+      for (int b = 0; b < n_box; ++b) tma_load_2d(smem + kShortOffV + b * kKVBytes, &tm_kv, bar_v, vcol, t0 + b * kKT);
+
+      const uint32_t idesc_s = make_idesc_bf16(kQT, (uint32_t)n_mma);   // S[128 x n] = Q[128 x 64] K[n x 64]^T
+      const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);            // O[128 x 64] += P[128 x 16] V[16 x 64]
+      const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffQ));
+      const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffK));
+      const uint32_t v_base = smem_u32(smem + kShortOffV);
+      mbar_wait<0>(bar_q, 0, 31);
+      mbar_wait<0>(bar_k, 0, 32);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+      umma_commit(bar_s);
+      mbar_wait<0>(bar_p, 0, 33);
+      mbar_wait<0>(bar_v, 0, 34);
+      tc_fence_after();
+      for (int j = 0; j < n_mma / 16; ++j) {
+        // A = P tile j/4 (K-major, 32 B per 16 keys); B = V (MN-major): 16 keys = two 8-row groups = 2048 B
+        const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffP + (j >> 2) * kQBytes)) + 2 * (j & 3);
+        const uint64_t v_desc = make_smem_desc_mnmajor_sw128(v_base + j * 2048);
+        umma_bf16_ss(tmem_O, p_desc, v_desc, idesc_o, j != 0);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int qpos = q0 + row;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float kLog2e = 1.4426950408889634f;
+    const int n_chunks = (n_mma + 31) >> 5;   // 32-key chunks that hold keys the MMAs read
+    mbar_wait<0>(bar_s, 0, 35);
+    tc_fence_after();
+    // pass 1: row maximum
+    float mx = -INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+      tmem_ld_wait();
+      float sc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
+      add_bias32(sc, sBias, 32 * c - qpos + R, R, bstride);
+      const int lim = len - 32 * c;   // keys of this chunk inside the sequence
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < lim ? sc[j] : -INFINITY);
+    }
+    // pass 2: exponentials, row sum, P
+    const float mb = mx * kLog2e;
+    float l0 = 0.f, l1 = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+      tmem_ld_wait();
+      float sc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
+      add_bias32(sc, sBias, 32 * c - qpos + R, R, bstride);
+      const int lim = (qpos < len) ? len - 32 * c : 0;   // rows past the sequence contribute nothing
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = j < lim ? fast_exp2(fmaf(sc[j], kLog2e, -mb)) : 0.f;
+        const float p1 = j + 1 < lim ? fast_exp2(fmaf(sc[j + 1], kLog2e, -mb)) : 0.f;
+        l0 += p0;
+        l1 += p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      uint8_t* prow = smem + kShortOffP + (c >> 1) * kQBytes + row * 128;
+      const int h = c & 1;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int slot = (h * 4 + s4) ^ (row & 7);
+        *reinterpret_cast<uint4*>(prow + slot * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait<0>(bar_o, 0, 36);
+    tc_fence_after();
+    if (q0 + warp * 32 < len) {  // warp-uniform
+      const float inv = 1.f / (l0 + l1);
+      __nv_bfloat16* dst = out + (int64_t)(t0 + qpos) * ld_out + head * kHD;
+#pragma unroll
+      for (int c = 0; c < kHD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qpos < len) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(dst + c * 32)[i] = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens,
                         const float* bias_lut, int n_tokens, int n_seqs, int max_len, int n_heads, int d_kv,
-                        int max_distance, cudaStream_t stream) {
+                        int max_distance, cudaStream_t stream, bool latency) {
   RPX_REQUIRE(d_kv == kHD, RPX_ERR_UNSUPPORTED, "attention: d_kv=%d (only 64 is implemented)", d_kv);
   RPX_REQUIRE(n_seqs > 0 && max_len > 0 && n_tokens > 0, RPX_ERR_INVALID, "attention: empty batch");
   RPX_REQUIRE(n_seqs <= 65535 && n_heads <= 65535, RPX_ERR_UNSUPPORTED, "attention: grid limits exceeded");
@@ -402,6 +593,20 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
     configured = dev.device;
   }
   dim3 grid((max_len + kQT - 1) / kQT, n_heads, n_seqs);
+  if (latency && max_len <= kShortKeys) {
+    const size_t smem_short = 1024 + kShortOffBias + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
+    if (smem_short <= dev.smem_optin) {
+      static thread_local int configured_short = -1;
+      if (configured_short != dev.device) {
+        RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dev.smem_optin));
+        configured_short = dev.device;
+      }
+      RPX_CUDA_OK(launch_pdl(t5_attention_short_kernel, grid, dim3(kAttnThreads), smem_short, stream, pdl_enabled(), tm_q, tm_kv,
+                             out, cu_seqlens, bias_lut, n_heads, max_distance, inner));
+      return RPX_OK;
+    }
+  }
   RPX_CUDA_OK(launch_pdl(t5_attention_tc_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_enabled(), tm_q, tm_kv, out,
                          cu_seqlens, bias_lut, n_heads, max_distance, inner));
   return RPX_OK;

@@ -313,7 +313,7 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 2);
     RPX_TRY(launch_t5_attention(ws.qkv, ws.attn, ws.cu_tokens, e->bias_lut, T, S, max_len, c.num_heads, c.d_kv,
-                                c.rel_max_distance, st));
+                                c.rel_max_distance, st, true));
   }
   {
     Prof p(e, st, 3);

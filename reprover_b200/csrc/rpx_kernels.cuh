@@ -12,7 +12,7 @@ namespace rpx {
 // bias_lut [heads][2*max_distance+1] fp32, entry (delta + max_distance), delta = key - query clamped.
 int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens,
                         const float* bias_lut, int n_tokens, int n_seqs, int max_len, int n_heads, int d_kv,
-                        int max_distance, cudaStream_t stream);
+                        int max_distance, cudaStream_t stream, bool latency = false);
 
 // ---- rpx_elementwise.cu
 // ByT5 tokenisation of packed byte strings into packed token ids (byte + 3, EOS = 1 last,
