@@ -71,11 +71,11 @@ int get_device_info(DeviceInfo* out);
 // Debug timeline (rpx_debug_set_timeline): each 1-CTA GEMM launch gets the next 8-stamp slot of the buffer.
 unsigned long long* next_timeline_slot();
 
-// Programmatic dependent launch is used along the kernel chain of a latency-path encode (a few hundred
-// tokens: the kernels are short and their prologues are worth overlapping); re-indexing launches are
-// plain (measured: no gain there).  RPX_PDL=0 never, RPX_PDL=2 every encoder launch.
+// Programmatic dependent launch is used along the kernel chain of encode calls of up to 16 k tokens (the
+// kernels are short and their prologues are worth overlapping); full re-indexing chunks are launched
+// plainly (measured: neutral to -1 % there).  RPX_PDL=0 never, RPX_PDL=2 every encoder launch.
 bool pdl_enabled();
-void set_pdl_scope(bool on);  // per thread: true while a latency-path forward enqueues its kernels
+void set_pdl_scope(bool on);  // per thread: true while such a forward enqueues its kernels
 
 // Kernel launch with (optionally) the programmatic-stream-serialization attribute; see rpx_ptx.cuh.
 template <typename Kern, typename... Args>

@@ -295,6 +295,10 @@ struct Prof {
 // 128 tokens x 64 (FFN-up: 64 or 128) output columns with an 8-deep (6-deep) operand ring: 18-112 CTAs
 // pull the layer's 36 MB of weights in parallel.  K is never split, so every output element is still
 // accumulated over k in the same order as on the throughput path.
+// Calls of at most this many tokens run their kernel chain under programmatic dependent launch: at 4 k tokens
+// the re-indexing tiles gain 7 % (2.03 -> 1.89 ms), at 16 k 3-8 %, from 32 k on it is neutral to -1 % (A/B,
+// BASELINE config-5 rows, two runs each).
+constexpr int kPdlMaxTokens = 16384;
 constexpr int kLatBlockN = 64;
 constexpr int kLatStages = 8;
 
@@ -351,7 +355,7 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   struct PdlScope {
     explicit PdlScope(bool on) { set_pdl_scope(on); }
     ~PdlScope() { set_pdl_scope(false); }
-  } pdl_scope(latency);
+  } pdl_scope(latency || T <= kPdlMaxTokens);
   {
     Prof p(e, st, 0);
     RPX_TRY(launch_embed(ws.ids, e->emb, ws.h32, ws.h16, ws.ssA, T, P, T, D, st));
