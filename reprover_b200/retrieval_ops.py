@@ -83,7 +83,7 @@ class IndexHandle:
             return h
         if h is not None:
             h.close()
-        if len(cls._cache) >= 8:   # a process holds a handful of indexes; do not pin old ones forever
+        if len(cls._cache) >= 4:   # a process holds a handful of indexes; do not pin old ones forever
             cls._cache.pop(next(iter(cls._cache))).close()
         h = cls(emb)
         cls._cache[key] = h

@@ -75,18 +75,35 @@ class B200PremiseRetriever:
         self.model_name = model_name
         cfg, sd = load_hf_checkpoint(model_name)
         self.encoder = T5EncoderEngine(cfg, sd, device, max_tokens_per_call=max_tokens_per_call)
+        self._index_handle = None      # rpx_index over the bf16 copy of corpus_embeddings
+        self._index_source = None      # (tensor identity, version) the handle was built from
+        self._corpus_embeddings: Optional[torch.Tensor] = None
         self.corpus: Optional[Corpus] = None
-        self.corpus_embeddings: Optional[torch.Tensor] = None
+        self.corpus_embeddings = None
         self.embeddings_staled = True
         self.sharded_index = None
         self._tokenizer = None
-        self._index_handle = None      # rpx_index over the bf16 copy of corpus_embeddings
-        self._index_source = None      # (tensor identity, version) the handle was built from
 
     # ------------------------------------------------------------------ construction (reference :52-85)
     @classmethod
     def load_hf(cls, ckpt_path: str, max_seq_len: int, device, dtype=None) -> "B200PremiseRetriever":
         return cls(ckpt_path, 0.0, 0, max_seq_len, 100, device=device, dtype=dtype)
+
+    @property
+    def corpus_embeddings(self) -> Optional[torch.Tensor]:
+        """[N, D] embedding matrix, row i for `corpus.all_premises[i]` (reference attribute of the same name).
+        Assigning a new tensor drops the engine's handle on the old one."""
+        return self.__dict__.get("_corpus_embeddings")
+
+    @corpus_embeddings.setter
+    def corpus_embeddings(self, value: Optional[torch.Tensor]) -> None:
+        if value is not self.__dict__.get("_corpus_embeddings"):
+            handle = self.__dict__.get("_index_handle")
+            if handle is not None:
+                handle.close()
+            self.__dict__["_index_handle"] = None
+            self.__dict__["_index_source"] = None
+        self.__dict__["_corpus_embeddings"] = value
 
     @property
     def tokenizer(self):

@@ -15,6 +15,7 @@ ap.add_argument("--premises", type=int, default=512)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--nq", type=int, default=1024)
 ap.add_argument("--n", type=int, default=200_000)
+ap.add_argument("--seed", type=int, default=1000)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 if args.mode in ("encode", "both"):
@@ -25,7 +26,7 @@ if args.mode in ("encode", "both"):
         eng.encode_bytes(data, offsets, 512)
     torch.cuda.synchronize()
 if args.mode in ("retrieve", "both"):
-    E = synth.random_unit_rows(args.n, 1472, 1000, dev)
+    E = synth.random_unit_rows(args.n, 1472, args.seed, dev)
     Q = synth.random_unit_rows(args.nq, 1472, 999, dev)
     for _ in range(args.warm + 1):
         sim_topk(Q, E, 100)
