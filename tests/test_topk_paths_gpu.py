@@ -71,6 +71,20 @@ def test_streaming_path_with_access_mask_skips_hidden_rows(rpx_lib, cuda_device)
     _check(Q, E, k, MMA, mask_words=words)
 
 
+def test_streaming_path_full_size_like_the_provers_call(rpx_lib, cuda_device):
+    """BASELINE-sized index (200k x 1472), ONE state, k = 100, a realistic access mask (imports = long runs
+    of files, plus a prefix of the own file): the shape `retrieve()` runs at (retrieval/model.py:338-375)."""
+    n, d, k = 200_000, 1472, 100
+    E, Q = _unit(n, d, 61, cuda_device), _unit(1, d, 62, cuda_device)
+    m = np.zeros((1, n), dtype=bool)
+    m[0, : 150_000] = True          # everything imported ...
+    m[0, 40_000:55_000] = False     # ... except a few files that are not
+    m[0, 150_000:150_037] = True    # premises of the own file before the theorem
+    h = _check(Q, E, k, AUTO, mask_words=_pack_mask(m))
+    assert h.stats()["n_exact"] == 0
+    _check(Q, h, k, AUTO)           # and without a mask, through the same handle
+
+
 @pytest.mark.parametrize("flags,nq", [(MMA, 1), (MMA, 4), (MMA, 130), (EXACT, 3), (AUTO, 5)])
 def test_forced_paths_agree_with_oracle(rpx_lib, cuda_device, flags, nq):
     _check(_unit(nq, 1472, 7, cuda_device), _unit(9001, 1472, 8, cuda_device), 100, flags)
