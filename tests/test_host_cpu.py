@@ -479,3 +479,110 @@ def test_index_written_by_the_reference_code_loads(tmp_path):
     fresh = Corpus(str(jsonl))
     for path, pos in [("Gold/F1.lean", Pos(8, 0)), ("Gold/F0.lean", Pos(27, 0)), ("Gold/F1.lean", Pos(999, 0))]:
         assert (r.corpus.accessible_mask_words(path, pos) == fresh.accessible_mask_words(path, pos)).all()
+
+
+def _toy_files():
+    def P(path, i):
+        return Premise(path, f"N.{path[:-5]}.l{i}", Pos(10 * i + 1, 0), Pos(10 * i + 5, 0), f"theorem l{i} : True := trivial")
+    return [(File("A.lean", [P("A.lean", 0), P("A.lean", 1)]), []),
+            (File("Empty.lean", []), []),                       # a file without premises ...
+            (File("B.lean", [P("B.lean", 0)]), ["A.lean", "Empty.lean"]),   # ... imported by a later one
+            (File("C.lean", [P("C.lean", 0), P("C.lean", 1)]), ["B.lean"])]
+
+
+def test_index_export_in_the_reference_layout_roundtrips(tmp_path):
+    """`dump_reference_index` writes GLOBALs `common.*` / `lean_dojo.Pos` (what a stock checkout unpickles,
+    retrieval/model.py:81-85) without leaving those modules behind, and `load_reference_index` reads the file
+    back to an equal corpus — including a premise-less file that a later file imports (the order the compat
+    loader used to get wrong)."""
+    import io
+    import pickletools
+    import sys
+
+    from reprover_b200.compat import dump_reference_index, load_reference_index
+
+    corpus = Corpus.from_files(_toy_files())
+    emb = torch.arange(5 * 8, dtype=torch.float32).reshape(5, 8)
+    buf = io.BytesIO()
+    dump_reference_index(corpus, emb.to(torch.bfloat16), buf)
+    assert "common" not in sys.modules and "lean_dojo" not in sys.modules
+    names = {arg for op, arg, _ in pickletools.genops(buf.getvalue()) if op.name == "SHORT_BINUNICODE"}
+    assert {"common", "lean_dojo", "IndexedCorpus", "Corpus", "File", "Premise", "Pos", "networkx.classes.digraph"} <= names
+    assert not any(str(n).startswith("reprover_b200") for n in names)
+    with pytest.raises((ModuleNotFoundError, AttributeError)):
+        pickle.loads(buf.getvalue())                       # only loadable where the reference's classes exist ...
+    back = load_reference_index(buf.getvalue())            # ... or through the compat loader
+    assert back.embeddings.dtype == torch.float32 and torch.equal(back.embeddings, emb.to(torch.bfloat16).float())
+    assert [(p.path, p.full_name, p.start, p.end, p.code) for p in back.corpus.all_premises] == \
+           [(p.path, p.full_name, p.start, p.end, p.code) for p in corpus.all_premises]
+    assert [f.path for f in back.corpus.files] == ["A.lean", "Empty.lean", "B.lean", "C.lean"]
+    for path in ("A.lean", "B.lean", "C.lean"):
+        assert back.corpus.get_dependencies(path) == corpus.get_dependencies(path)
+        assert (back.corpus.accessible_mask_words(path, Pos(12, 0)) == corpus.accessible_mask_words(path, Pos(12, 0))).all()
+    # the retriever's load_corpus takes the same file
+    path = tmp_path / "idx.pickle"
+    path.write_bytes(buf.getvalue())
+    r = _stub_retriever(10**9)
+    r.load_corpus(str(path))
+    assert not r.embeddings_staled and len(r.corpus) == 5 and "Empty.lean" in r.corpus
+
+
+def test_compat_file_order_falls_back_to_a_topological_sort():
+    """A reference pickle whose graph nodes are not in import order still converts (imports first, premise
+    order kept); a cycle is reported."""
+    import networkx as nx
+
+    from reprover_b200 import compat
+
+    fa = compat._RefFile(); fa.__dict__.update(path="A.lean", premises=[])
+    pb = compat._RefPremise()
+    pos = compat._RefPos(); pos.__dict__.update(line_nb=1, column_nb=0)
+    pb.__dict__.update(path="B.lean", full_name="B.x", start=pos, end=pos, code="def x := 1")
+    fb = compat._RefFile(); fb.__dict__.update(path="B.lean", premises=[pb])
+    g = nx.DiGraph()
+    g.add_node("B.lean", file=fb)          # importer first: not an import order
+    g.add_node("A.lean", file=fa)
+    g.add_edge("B.lean", "A.lean")
+    ref_corpus = compat._RefCorpus(); ref_corpus.__dict__.update(transitive_dep_graph=g, all_premises=[pb])
+    c = compat.convert_corpus(ref_corpus)
+    assert [f.path for f in c.files] == ["A.lean", "B.lean"] and c.get_dependencies("B.lean") == ["A.lean"]
+    g.add_edge("A.lean", "B.lean")
+    with pytest.raises(ValueError, match="cycle"):
+        compat.convert_corpus(ref_corpus)
+
+
+def test_corpus_embeddings_assignment_drops_the_index_handle():
+    class _Handle:
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    r = _stub_retriever(10**9)
+    h = _Handle()
+    r._index_handle, r._index_source = h, (1, 0)
+    same = r.corpus_embeddings
+    r.corpus_embeddings = same                     # same object: nothing to invalidate
+    assert r._index_handle is h and not h.closed
+    r.corpus_embeddings = torch.zeros(2, 8)
+    assert r._index_handle is None and h.closed
+
+
+def test_checkpoint_and_k_errors_are_explicit(tmp_path):
+    from reprover_b200.engine import load_hf_checkpoint, required_weight_keys
+    from reprover_b200.retrieval_ops import _check_k
+
+    with pytest.raises(FileNotFoundError, match="neither a local checkpoint directory nor a hub snapshot"):
+        load_hf_checkpoint("no-such-org/no-such-retriever-checkpoint")
+    (tmp_path / "weights.bin").write_bytes(b"x")
+    with pytest.raises(FileNotFoundError, match="DIRECTORY"):
+        load_hf_checkpoint(str(tmp_path / "weights.bin"))
+    (tmp_path / "ck").mkdir()
+    with pytest.raises(FileNotFoundError, match="config.json"):
+        load_hf_checkpoint(str(tmp_path / "ck"))
+    keys = required_weight_keys({"num_layers": 2})
+    assert len(keys) == 2 + 2 * 9 and "encoder.block.1.layer.1.DenseReluDense.wo.weight" in keys
+    for bad in (0, -3, 1025, 2.5):
+        with pytest.raises(ValueError, match="premises per query"):
+            _check_k(bad)
+    _check_k(1), _check_k(1024)
