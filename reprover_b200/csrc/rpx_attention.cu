@@ -99,7 +99,11 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                        __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens,
                        const float* __restrict__ bias_lut, int n_heads, int R, int ld_out) {
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
-  pdl_wait();  // qkv comes from the preceding GEMM (cu_seqlens / bias_lut are older, but one wait covers all)
+  // Under programmatic dependent launch this CTA may start while the QKV projection is still running.
+  // cu_seqlens and bias_lut were complete before the first kernel of the chain started, so the whole
+  // prologue (bias table, barriers, TMEM) runs ahead; only the driver thread's TMA loads of q / k / v wait
+  // for the predecessor (pdl_wait below).  The softmax warps touch global memory only to store `out`, after
+  // MMAs that consumed those loads.
   pdl_launch_dependents();
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;
@@ -159,6 +163,7 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     // ------------------------------------------------------------------ TMA + MMA driver (one thread)
     if (elect_one()) {
       const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
+      pdl_wait();
       mbar_arrive_expect_tx(bar_q, kQBytes);
       tma_load_2d(smem + kOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
       mbar_arrive_expect_tx(bar_k_full, kKVBytes);
@@ -399,8 +404,7 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
                           __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens,
                           const float* __restrict__ bias_lut, int n_heads, int R, int ld_out) {
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
-  pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // (prologue ahead of the predecessor's end: see t5_attention_tc_kernel)
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;   // <= kShortKeys (checked by the launcher through max_len)
   const int q0 = qt * kQT;
@@ -453,6 +457,7 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   if (warp == 4) {
     if (elect_one()) {
       const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
+      pdl_wait();
       mbar_arrive_expect_tx(bar_q, kQBytes);
       tma_load_2d(smem + kShortOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
       mbar_arrive_expect_tx(bar_k, (uint32_t)(n_box * kKVBytes));
