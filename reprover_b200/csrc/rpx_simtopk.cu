@@ -478,7 +478,8 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
       (reinterpret_cast<uintptr_t>(seg_off + n_seg + 1) + 15) & ~(uintptr_t)15);                   // [n_seg * list_max]
   __shared__ uint64_t red64[32];
   __shared__ float redf[32];
-  __shared__ int cslots[3];
+  __shared__ int hist[256];
+  __shared__ int sel_bin, sel_above;
   __shared__ int n_sel;
   __shared__ double kth_score;
   __shared__ uint32_t kth_idx;
@@ -489,7 +490,6 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
 
   for (int i = tid; i < d / 8; i += kSelThreads)
     reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(Q + (size_t)q * d)[i];
-  if (tid < 3) cslots[tid] = 0;
   if (tid == 0) n_sel = 0;
   // list lengths and final thresholds of the query's segments (independent loads, one per thread)
   float tdrop = -INFINITY;
@@ -528,23 +528,57 @@ select_rescore_kernel(const uint2* __restrict__ cand, const int32_t* __restrict_
   kmin = block_reduce<uint64_t>(kmin, red64, [](uint64_t a, uint64_t b) { return a < b ? a : b; }, ~0ull);
   kmax = block_reduce<uint64_t>(kmax, red64, [](uint64_t a, uint64_t b) { return a > b ? a : b; }, 0ull);
 
-  // ---- threshold: count(key >= lo) in [n_res, n_res + 16] (keys are distinct, so it exists)
+  // ---- threshold: count(key >= lo) in [n_res, n_res + kSelSlack] (keys are distinct, so it exists).
+  // Radix descent over the window [base, win_hi] of the key space that still holds the boundary: 256
+  // equal bins, a shared-memory histogram, a warp scan from the top bin down to the bin where the count
+  // crosses what is still needed; that bin becomes the next window.  Candidate keys cluster in a narrow
+  // score range, so the window is sized from (kmin, kmax) instead of the 64-bit digit positions: two or
+  // three levels where a bisection takes ~30 counting rounds.
   uint64_t lo = kmin;
   if (total > n_res + kSelSlack) {
-    uint64_t hi = kmax;  // count(>= kmax) = 1 < n_res
-    int count_lo = total;
-    // invariant: count(>= lo) = count_lo >= n_res, count(>= hi) < n_res
-    for (int iter = 0; count_lo > n_res + kSelSlack && hi - lo > 1; ++iter) {
-      const uint64_t mid = lo + (hi - lo) / 2;
-      int m = 0;
-      for (int i = tid; i < total; i += kSelThreads) m += keys[i] >= mid ? 1 : 0;
-      m = block_count(m, cslots, iter);
-      if (m >= n_res) {
-        lo = mid;
-        count_lo = m;
-      } else {
-        hi = mid;
+    uint64_t base = kmin, win_hi = kmax;
+    int need = n_res;  // keys still to take from the window; everything above the window is taken
+    int shift = 64 - __clzll((long long)((kmax - kmin) | 1ull)) - 8;
+    shift = shift < 0 ? 0 : shift;
+    for (;;) {
+      for (int b = tid; b < 256; b += kSelThreads) hist[b] = 0;
+      __syncthreads();
+      for (int i = tid; i < total; i += kSelThreads) {
+        const uint64_t key = keys[i];
+        if (key >= base && key <= win_hi) atomicAdd(&hist[(int)((key - base) >> shift)], 1);
       }
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns bins [8l, 8l + 8); suf = keys in the bins of lanes >= l
+        int own = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) own += hist[8 * lane + j];
+        int suf = own;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int v = __shfl_down_sync(kFull, suf, off);
+          if (lane + off < 32) suf += v;
+        }
+        // the crossing lane: suf >= need while the lanes above it hold fewer than need
+        if (suf >= need && suf - own < need) {
+          int above = suf - own, b = 8 * lane + 7;
+          for (; b > 8 * lane; --b) {
+            if (above + hist[b] >= need) break;
+            above += hist[b];
+          }
+          sel_bin = b;
+          sel_above = above;
+        }
+      }
+      __syncthreads();
+      const int b = sel_bin, above = sel_above, in_bin = hist[b];
+      lo = base + ((uint64_t)b << shift);
+      if (above + in_bin <= need + kSelSlack || shift == 0) break;
+      need -= above;
+      base = lo;
+      win_hi = base + ((1ull << shift) - 1ull);
+      shift = shift > 8 ? shift - 8 : 0;
+      __syncthreads();  // hist / sel_bin are rewritten by the next level
     }
   }
   // ---- collect the selected candidates
