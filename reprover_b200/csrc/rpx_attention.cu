@@ -386,18 +386,28 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-shot variant for short sequences (<= 256 keys) on the encoder's latency path: one proof
-// state is 2 query tiles x 6 heads = 12 CTAs, and with the streaming kernel above each of them walks 4
-// dependent key steps (S MMA -> softmax -> PV MMA, ~2.5 us each).  Here the whole key range is one step:
-// S[128 x 256] in TMEM from ONE group of N = 256 MMAs, a two-pass softmax straight out of TMEM (no running
-// maximum, no O rescale), P as four 128 x 64 K-major tiles, O from one run of PV MMAs.  One CTA per SM
-// (the accumulators take 320 of the 512 TMEM columns) — irrelevant at 12 CTAs.
+// Single-shot variant for short sequences (<= 256 keys) on the encoder's latency path.  One proof state
+// is a handful of (128-query tile, head) pairs — 12 CTAs on a 148-SM machine — and in each of them one warp
+// walks the whole key range of its 32 rows twice (row maximum, then exponentials): that walk, not the
+// tensor core, is the critical path.  Here a CTA takes 32 QUERIES and all four softmax warps work on them:
+//   * the 32 query rows are loaded FOUR times, into row groups 0-31 / 32-63 / 64-95 / 96-127 of the Q tile,
+//     so S[128 x keys] = Q K^T (one group of N <= 256 MMAs, the whole key range at once) holds the same 32
+//     score rows in all four TMEM lane groups — a warp can only read its own lane group;
+//   * warp w handles the 32-key chunks w and w + 4 of those rows: maximum and sum are combined across
+//     the warps through shared memory (two named-barrier syncs), each warp writes its chunks of P;
+//   * O = P V from one run of MMAs; only rows 0-31 of P / O mean anything, warp 0 stores them.
+// No running maximum, no O rescale.  Four times the CTAs (48 for a 225-token state), a quarter of the
+// serial softmax work in each.
 constexpr int kShortKeys = 256;
+constexpr int kShortQ = 32;                                          // queries per CTA
 constexpr int kShortOffQ = 0;
 constexpr int kShortOffK = kQBytes;                                  // [256 keys][64 bf16]
 constexpr int kShortOffV = kQBytes + kShortKeys * 128;
 constexpr int kShortOffP = kQBytes + 2 * kShortKeys * 128;           // 4 tiles of [128 rows][64 keys]
-constexpr int kShortOffBias = kShortOffP + 4 * kQBytes;
+constexpr int kShortOffRed = kShortOffP + 4 * kQBytes;               // max[4][32], sum[4][32] floats
+constexpr int kShortOffBias = kShortOffRed + 2 * 4 * 32 * 4;
+
+RPX_DEVICE void softmax_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -407,12 +417,14 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   pdl_launch_dependents();   // (prologue ahead of the predecessor's end: see t5_attention_tc_kernel)
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;   // <= kShortKeys (checked by the launcher through max_len)
-  const int q0 = qt * kQT;
+  const int q0 = qt * kShortQ;
   if (q0 >= len) return;  // whole CTA
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  float* sMax = reinterpret_cast<float*>(smem + kShortOffRed);   // [4][32]
+  float* sSum = sMax + 4 * 32;                                   // [4][32]
   float* sBias = reinterpret_cast<float*>(smem + kShortOffBias);
   const int lut_w = 2 * R + 1;
   const int bstride = bias_copy_stride(R);
@@ -459,7 +471,8 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
       pdl_wait();
       mbar_arrive_expect_tx(bar_q, kQBytes);
-      tma_load_2d(smem + kShortOffQ, &tm_q, bar_q, head * kHD, t0 + q0);
+      for (int g = 0; g < 4; ++g)   // the same 32 query rows into every row group of the tile
+        tma_load_2d(smem + kShortOffQ + g * kShortQ * 128, &tm_q, bar_q, head * kHD, t0 + q0);
       mbar_arrive_expect_tx(bar_k, (uint32_t)(n_box * kKVBytes));
       for (int b = 0; b < n_box; ++b) tma_load_2d(smem + kShortOffK + b * kKVBytes, &tm_kv, bar_k, kcol, t0 + b * kKT);
       mbar_arrive_expect_tx(bar_v, (uint32_t)(n_box * kKVBytes));
@@ -488,16 +501,16 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       umma_commit(bar_o);
     }
   } else {
-    const int row = warp * 32 + lane;
-    const int qpos = q0 + row;
+    // query row `lane` of the CTA; this warp's copy of its scores sits in TMEM lanes [32 warp, 32 warp + 32)
+    const int qpos = q0 + lane;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float kLog2e = 1.4426950408889634f;
     const int n_chunks = (n_mma + 31) >> 5;   // 32-key chunks that hold keys the MMAs read
     mbar_wait<0>(bar_s, 0, 35);
     tc_fence_after();
-    // pass 1: row maximum
+    // pass 1: maximum over this warp's chunks, then over the warps
     float mx = -INFINITY;
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = warp; c < n_chunks; c += 4) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
       tmem_ld_wait();
@@ -509,10 +522,13 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < lim ? sc[j] : -INFINITY);
     }
+    sMax[warp * 32 + lane] = mx;
+    softmax_warps_sync();
+    mx = fmaxf(fmaxf(sMax[lane], sMax[32 + lane]), fmaxf(sMax[64 + lane], sMax[96 + lane]));  // (chunk 0 is never empty)
     // pass 2: exponentials, row sum, P
     const float mb = mx * kLog2e;
     float l0 = 0.f, l1 = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = warp; c < n_chunks; c += 4) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
       tmem_ld_wait();
@@ -530,27 +546,29 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         l1 += p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
-      uint8_t* prow = smem + kShortOffP + (c >> 1) * kQBytes + row * 128;
+      // P row `lane` (rows 32-127 of the tiles are never written: their O rows are never read)
+      uint8_t* prow = smem + kShortOffP + (c >> 1) * kQBytes + lane * 128;
       const int h = c & 1;
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
-        const int slot = (h * 4 + s4) ^ (row & 7);
+        const int slot = (h * 4 + s4) ^ (lane & 7);
         *reinterpret_cast<uint4*>(prow + slot * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
       }
     }
+    sSum[warp * 32 + lane] = l0 + l1;
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_p);
 
-    mbar_wait<0>(bar_o, 0, 36);
-    tc_fence_after();
-    if (q0 + warp * 32 < len) {  // warp-uniform
-      const float inv = 1.f / (l0 + l1);
+    if (warp == 0) {
+      mbar_wait<0>(bar_o, 0, 36);   // (PV needed every warp's P, so every warp's partial sum is in sSum as well)
+      tc_fence_after();
+      const float inv = 1.f / ((sSum[lane] + sSum[32 + lane]) + (sSum[64 + lane] + sSum[96 + lane]));
       __nv_bfloat16* dst = out + (int64_t)(t0 + qpos) * ld_out + head * kHD;
 #pragma unroll
       for (int c = 0; c < kHD / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+        tmem_ld_32x32(tmem_O + c * 32, v);
         tmem_ld_wait();
         if (qpos < len) {
 #pragma unroll
@@ -588,8 +606,24 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   CUtensorMap tm_q, tm_kv;
-  RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kQT));
   RPX_TRY(make_tmap_bf16_2d(&tm_kv, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kKT));
+  if (latency && max_len <= kShortKeys) {
+    const size_t smem_short = 1024 + kShortOffBias + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
+    if (smem_short <= dev.smem_optin) {
+      RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kShortQ));
+      static thread_local int configured_short = -1;
+      if (configured_short != dev.device) {
+        RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dev.smem_optin));
+        configured_short = dev.device;
+      }
+      const dim3 grid32((max_len + kShortQ - 1) / kShortQ, n_heads, n_seqs);
+      RPX_CUDA_OK(launch_pdl(t5_attention_short_kernel, grid32, dim3(kAttnThreads), smem_short, stream, pdl_enabled(), tm_q,
+                             tm_kv, out, cu_seqlens, bias_lut, n_heads, max_distance, inner));
+      return RPX_OK;
+    }
+  }
+  RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kQT));
   const size_t smem = 1024 + kAttnSmemFixed + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
   RPX_REQUIRE(smem <= 100 * 1024, RPX_ERR_UNSUPPORTED, "attention: bias table too large (%zu B of shared memory)", smem);
   static thread_local int configured = -1;
@@ -597,21 +631,7 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
     RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = dev.device;
   }
-  dim3 grid((max_len + kQT - 1) / kQT, n_heads, n_seqs);
-  if (latency && max_len <= kShortKeys) {
-    const size_t smem_short = 1024 + kShortOffBias + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
-    if (smem_short <= dev.smem_optin) {
-      static thread_local int configured_short = -1;
-      if (configured_short != dev.device) {
-        RPX_CUDA_OK(cudaFuncSetAttribute(t5_attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)dev.smem_optin));
-        configured_short = dev.device;
-      }
-      RPX_CUDA_OK(launch_pdl(t5_attention_short_kernel, grid, dim3(kAttnThreads), smem_short, stream, pdl_enabled(), tm_q, tm_kv,
-                             out, cu_seqlens, bias_lut, n_heads, max_distance, inner));
-      return RPX_OK;
-    }
-  }
+  const dim3 grid((max_len + kQT - 1) / kQT, n_heads, n_seqs);
   RPX_CUDA_OK(launch_pdl(t5_attention_tc_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_enabled(), tm_q, tm_kv, out,
                          cu_seqlens, bias_lut, n_heads, max_distance, inner));
   return RPX_OK;

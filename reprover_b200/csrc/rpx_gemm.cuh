@@ -400,12 +400,17 @@ struct EpiStoreBF16 {
   static constexpr size_t kSmemBytes = 0;
   static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
+  float rs = 0.f;  // this thread's row scale for the tile in flight
   __device__ EpiStoreBF16(const Params& p_, uint8_t*, int, int) : p(p_) {}
-  __device__ void before_wait(const TileCtx&) {}
+  // the row scale does not depend on the accumulator: its partial sums (up to 23 L2 round trips on the latency
+  // path) are fetched while the MMAs of the tile are still running
+  __device__ void before_wait(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    rs = m < t.M ? p.rs.get(m) : 0.f;
+  }
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
-    const float rs = ok ? p.rs.get(m) : 0.f;
     for (int c = 32 * t.part; c < t.n_cols; c += 32 * t.split) {
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
@@ -455,21 +460,27 @@ struct EpiResidual {
   Params p;
   float4* stg;  // this warp's staging tile: row r = 8 float4, stored at slot (j ^ (r & 7))
   int lane, grp;
+  float4 h[8];  // residual values of the chunk in flight (loaded one chunk ahead)
   __device__ EpiResidual(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
     lane = row & 31;
     grp = row >> 5;
     stg = reinterpret_cast<float4*>(smem_extra) + (part * 4 + grp) * 32 * 8;
   }
-  __device__ void before_wait(const TileCtx&) {}
   __device__ __forceinline__ void load_chunk(const TileCtx& t, int c, int row_base, int sub, int col4,
-                                             float4 (&h)[8]) const {
+                                             float4 (&hh)[8]) const {
     const size_t col = (size_t)t.n0 + c + col4;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = row_base + sub + 4 * i;
-      if (m < t.M) h[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
-      else h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < t.M) hh[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
+      else hh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  // the first chunk's residual values do not depend on the accumulator: they are fetched while the MMAs of
+  // the tile are still running (on the latency path that L2 round trip was a third of the epilogue)
+  __device__ void before_wait(const TileCtx& t) {
+    const int c = 32 * t.part;
+    if (c < t.n_cols) load_chunk(t, c, t.m0 + grp * 32, lane >> 3, (lane & 7) * 4, h);
   }
   __device__ void tile(const TileCtx& t) {
     const int sub = lane >> 3;        // row within a group of 4
@@ -480,9 +491,8 @@ struct EpiResidual {
     float ss[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss[i] = 0.f;
-    float4 h[8], hn[8];
+    float4 hn[8];
     int c = 32 * t.part;
-    if (c < t.n_cols) load_chunk(t, c, row_base, sub, col4, h);
     for (; c < t.n_cols; c += step) {
       uint32_t v[32];
       tmem_ld_32x32(t.tmem + c, v);
@@ -673,12 +683,15 @@ struct EpiGeGLUT {
   static constexpr size_t kSmemBytes = 0;
   static constexpr int kWarps = RPX_EPI_WARPS;
   Params p;
+  float rs = 0.f;  // (fetched ahead of the accumulator: see EpiStoreBF16)
   __device__ EpiGeGLUT(const Params& p_, uint8_t*, int, int) : p(p_) {}
-  __device__ void before_wait(const TileCtx&) {}
+  __device__ void before_wait(const TileCtx& t) {
+    const int m = t.m0 + t.row;
+    rs = m < t.M ? p.rs.get(m) : 0.f;
+  }
   __device__ void tile(const TileCtx& t) {
     const int m = t.m0 + t.row;
     const bool ok = m < t.M;
-    const float rs = ok ? p.rs.get(m) : 0.f;
     for (int c = 32 * t.part; c < HALF; c += 32 * t.split) {
       uint32_t g[32], u[32];
       tmem_ld_32x32(t.tmem + c, g);

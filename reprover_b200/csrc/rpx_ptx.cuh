@@ -249,6 +249,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- thread-block clusters: rank, barrier
+RPX_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// All threads of all CTAs of the cluster; release/acquire at cluster scope.
+RPX_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // Kernels of one encoder call are launched with programmatic stream serialization (rpx_common.cuh
 // launch_pdl): a kernel may start while its predecessor in the stream is still running, so that its

@@ -8,6 +8,8 @@ from reprover_b200.engine import T5EncoderEngine
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 225
 dev = torch.device("cuda:0"); cfg = dict(synth.BYT5_SMALL)
+if len(sys.argv) > 2:
+    cfg["num_layers"] = int(sys.argv[2])   # few layers: all weights stay in L2 between encodes
 eng = T5EncoderEngine(cfg, synth.random_t5_state_dict(cfg, seed=synth.SEED), dev); eng.set_latency_tokens(4096)
 d = torch.from_numpy(np.random.default_rng(0).integers(32, 120, size=T - 1, dtype=np.uint8)).to(dev)
 o = torch.empty(1, 1472, dtype=torch.bfloat16, device=dev)
@@ -16,7 +18,7 @@ for _ in range(5):
     eng.encode_packed_bytes(d, offs, 4096, o)
 torch.cuda.synchronize()
 lib = _native.load()
-n = 48
+n = min(48, 4 * cfg["num_layers"])
 buf = torch.zeros(n, 8, dtype=torch.int64, device=dev)
 lib.rpx_debug_set_timeline(buf.data_ptr(), n)
 eng.encode_packed_bytes(d, offs, 4096, o)
