@@ -189,64 +189,98 @@ __global__ void pool_normalize_kernel(const float* __restrict__ h32, const float
   }
 }
 
-// Latency-path variant (one or a few sequences per call): the kernel above walks a sequence's tokens one
-// after the other in a single CTA — 56 dependent trips for a 225-token proof state, 0.13 ms, a quarter of the
-// whole single-state encode.  Here the 16 warps of the CTA take the tokens round-robin (lanes across the
-// row: 16-byte loads, 12 per lane per token, all in flight together), and the 16 partial rows are combined
-// in warp order.  (Not bit-identical to the sequential order above, like the rest of the latency path.)
-constexpr int kPoolWideWarps = 16;
-__global__ void __launch_bounds__(kPoolWideWarps * 32)
-pool_normalize_wide_kernel(const float* __restrict__ h32, const float* __restrict__ ss, int ss_stride, int n_parts,
-                           const float* __restrict__ ln_w, const int32_t* __restrict__ cu_tokens,
-                           void* __restrict__ out, int out_dtype, int d_model, float eps) {
-  pdl_wait();
+// Latency-path variant (one or a few sequences per call).  The kernel above walks a sequence's tokens one
+// after the other in a single CTA: 56 dependent trips for a 225-token proof state, and one SM pulling the
+// whole 1.3 MB of final hidden states — a tenth of the single-state encode.  Here the pooling is two short
+// kernels:
+//   pool_partial_kernel   one CTA per GROUP of 16 consecutive tokens of a sequence, one warp per token (lanes
+//                         across the row, every 16-byte load of the row in flight at once; the row's RMSNorm
+//                         partial sums fetched lane-parallel); the 16 scaled rows are added in token order and
+//                         the group's row goes to `scratch[first token of the sequence + group]`;
+//   pool_final_kernel     one CTA per sequence adds its group rows in group order, applies the final RMSNorm
+//                         weight and the mean, L2-normalises.
+// The grouping depends on the sequence alone, so a state's embedding does not depend on what it is batched
+// with.  (Not bit-identical to the sequential order above, like the rest of the latency path.)
+constexpr int kPoolGroup = 16;
+__global__ void __launch_bounds__(kPoolGroup * 32)
+pool_partial_kernel(const float* __restrict__ h32, const float* __restrict__ ss, int ss_stride, int n_parts,
+                    const int32_t* __restrict__ cu_tokens, float* __restrict__ scratch, int d_model, float eps) {
   pdl_launch_dependents();
-  extern __shared__ __align__(16) float part[];  // [kPoolWideWarps][d_model]
+  extern __shared__ __align__(16) float part[];  // [kPoolGroup][d_model]
+  const int s = blockIdx.y, g = blockIdx.x;
+  const int t0 = cu_tokens[s], t1 = cu_tokens[s + 1];   // (written before the first kernel of the chain)
+  if (t0 + g * kPoolGroup >= t1) return;
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = d_model >> 2;
+  const int t = t0 + g * kPoolGroup + warp;
+  constexpr int kMaxIt = 16;  // d_model <= 16 * 32 * 4 = 2048 (checked by the launcher)
+  if (t < t1) {
+    const float4* row = reinterpret_cast<const float4*>(h32 + (int64_t)t * d_model);
+    float4 v[kMaxIt];
+#pragma unroll
+    for (int i = 0; i < kMaxIt; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < n4 ? row[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float sum = 0.f;
+    for (int p = lane; p < n_parts; p += 32) sum += ss[(int64_t)p * ss_stride + t];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float rs = rsqrtf(sum * (1.0f / (float)d_model) + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxIt; ++i) {
+      const int c = lane + 32 * i;
+      if (c < n4)
+        reinterpret_cast<float4*>(part + (size_t)warp * d_model)[c] = make_float4(v[i].x * rs, v[i].y * rs, v[i].z * rs, v[i].w * rs);
+    }
+  }
+  __syncthreads();
+  const int n_rows = min(kPoolGroup, t1 - (t0 + g * kPoolGroup));
+  for (int i = threadIdx.x; i < n4; i += kPoolGroup * 32) {
+    float4 tot = reinterpret_cast<const float4*>(part)[i];
+    for (int w = 1; w < n_rows; ++w) {
+      const float4 a = reinterpret_cast<const float4*>(part + (size_t)w * d_model)[i];
+      tot.x += a.x;
+      tot.y += a.y;
+      tot.z += a.z;
+      tot.w += a.w;
+    }
+    reinterpret_cast<float4*>(scratch + (int64_t)(t0 + g) * d_model)[i] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+pool_final_kernel(const float* __restrict__ scratch, const float* __restrict__ ln_w, const int32_t* __restrict__ cu_tokens,
+                  void* __restrict__ out, int out_dtype, int d_model) {
+  pdl_launch_dependents();
   __shared__ float red[32];
   const int s = blockIdx.x;
   const int t0 = cu_tokens[s], t1 = cu_tokens[s + 1];
+  const int n_groups = (t1 - t0 + kPoolGroup - 1) / kPoolGroup;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n4 = d_model >> 2;
-  constexpr int kMaxIt = 16;  // d_model <= 16 * 32 * 4 = 2048 (checked by the launcher)
-  float4 acc[kMaxIt];
-#pragma unroll
-  for (int i = 0; i < kMaxIt; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float inv_d = 1.0f / (float)d_model;
-  for (int t = t0 + warp; t < t1; t += kPoolWideWarps) {
-    float sum = 0.f;
-    for (int p = 0; p < n_parts; ++p) sum += ss[(int64_t)p * ss_stride + t];
-    const float rs = rsqrtf(sum * inv_d + eps);
-    const float4* row = reinterpret_cast<const float4*>(h32 + (int64_t)t * d_model);
-#pragma unroll
-    for (int g = 0; g < kMaxIt; g += 4) {  // four 16-byte loads per lane in flight
-      float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane + 32 * (g + j);
-        v[j] = c < n4 ? row[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[g + j].x = fmaf(v[j].x, rs, acc[g + j].x);
-        acc[g + j].y = fmaf(v[j].y, rs, acc[g + j].y);
-        acc[g + j].z = fmaf(v[j].z, rs, acc[g + j].z);
-        acc[g + j].w = fmaf(v[j].w, rs, acc[g + j].w);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kMaxIt; ++i) {
-    const int c = lane + 32 * i;
-    if (c < n4) reinterpret_cast<float4*>(part + (size_t)warp * d_model)[c] = acc[i];
-  }
-  __syncthreads();
-  const int i = threadIdx.x;
+  const int i = threadIdx.x, n4 = d_model >> 2;
   const bool active = i < n4;
+  pdl_wait();
   float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
   float sq = 0.f;
   if (active) {
-    for (int w = 0; w < kPoolWideWarps; ++w) {
-      const float4 a = reinterpret_cast<const float4*>(part + (size_t)w * d_model)[i];
+    const float4* src = reinterpret_cast<const float4*>(scratch + (int64_t)t0 * d_model) + i;
+    int g = 0;
+    for (; g + 8 <= n_groups; g += 8) {   // eight independent loads in flight, additions in group order
+      float4 a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = src[(size_t)(g + j) * n4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        tot.x += a[j].x;
+        tot.y += a[j].y;
+        tot.z += a[j].z;
+        tot.w += a[j].w;
+      }
+    }
+    for (; g < n_groups; ++g) {
+      const float4 a = src[(size_t)g * n4];
       tot.x += a.x;
       tot.y += a.y;
       tot.z += a.z;
@@ -264,7 +298,7 @@ pool_normalize_wide_kernel(const float* __restrict__ h32, const float* __restric
   if (lane == 0) red[warp] = sq;
   __syncthreads();
   if (threadIdx.x < 32) {
-    float v = threadIdx.x < kPoolWideWarps ? red[threadIdx.x] : 0.f;
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (threadIdx.x == 0) red[0] = v;
   }
@@ -329,19 +363,23 @@ int launch_embed(const int32_t* ids, const float* table, float* h32, __nv_bfloat
 
 int launch_pool_normalize(const float* h32, const float* ss, int ss_stride, int n_parts, const float* ln_w,
                           const int32_t* cu_tokens, void* out, int out_dtype, int n_seqs, int d_model,
-                          float eps, cudaStream_t stream, bool wide) {
+                          float eps, cudaStream_t stream, float* group_scratch, int max_len) {
   const int threads = (int)align_up((size_t)d_model / 4, 32);
   RPX_REQUIRE(d_model % 4 == 0 && threads <= 1024, RPX_ERR_UNSUPPORTED, "pool: unsupported d_model=%d", d_model);
   RPX_REQUIRE(out_dtype == RPX_DTYPE_BF16 || out_dtype == RPX_DTYPE_F32, RPX_ERR_INVALID, "pool: bad out dtype");
-  if (wide && d_model <= 2048 && d_model / 4 <= kPoolWideWarps * 32) {
-    const size_t smem = (size_t)kPoolWideWarps * d_model * sizeof(float);
+  // latency path: `group_scratch` holds one fp32 row per token index (a sequence uses the first
+  // ceil(len / 16) rows of its own token range)
+  if (group_scratch != nullptr && d_model <= 2048 && threads <= 512 && n_seqs <= 65535) {
+    const size_t smem = (size_t)kPoolGroup * d_model * sizeof(float);
     static thread_local bool configured = false;
     if (!configured) {
-      RPX_CUDA_OK(cudaFuncSetAttribute(pool_normalize_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      RPX_CUDA_OK(cudaFuncSetAttribute(pool_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
-    RPX_CUDA_OK(launch_pdl(pool_normalize_wide_kernel, dim3(n_seqs), dim3(kPoolWideWarps * 32), smem, stream, pdl_enabled(), h32,
-                           ss, ss_stride, n_parts, ln_w, cu_tokens, out, out_dtype, d_model, eps));
+    RPX_CUDA_OK(launch_pdl(pool_partial_kernel, dim3(ceil_div(max_len, kPoolGroup), n_seqs), dim3(kPoolGroup * 32), smem, stream,
+                           pdl_enabled(), h32, ss, ss_stride, n_parts, cu_tokens, group_scratch, d_model, eps));
+    RPX_CUDA_OK(launch_pdl(pool_final_kernel, dim3(n_seqs), dim3(threads), 0, stream, pdl_enabled(),
+                           (const float*)group_scratch, ln_w, cu_tokens, out, out_dtype, d_model));
     return RPX_OK;
   }
   RPX_CUDA_OK(launch_pdl(pool_normalize_kernel, dim3(n_seqs), dim3(threads), 0, stream, pdl_enabled(), h32, ss, ss_stride,

@@ -141,7 +141,7 @@ struct rpx_encoder {
   rpx_t5_config cfg;
   int inner = 0;
   int n_parts = 0;      // RMSNorm partial sums per row on the throughput path: one per 256-wide n-tile
-  int n_parts_lat = 0;  // ... on the latency path: one per 64-wide n-tile
+  int n_parts_lat = 0;  // ... on the latency path: one per 32-wide n-tile
   int latency_tokens = 0;  // calls with at most this many packed tokens take the latency path (0: never)
   size_t layer_bytes = 0;  // packed weights of one layer (qkv | o | wi | wo, contiguous from LayerW::qkv)
   const float* emb = nullptr;
@@ -300,6 +300,14 @@ struct Prof {
 // BASELINE config-5 rows, two runs each).
 constexpr int kPdlMaxTokens = 16384;
 constexpr int kLatBlockN = 64;
+// The two residual GEMMs of the latency path (O-proj, FFN down) up to 256 tokens: 32-wide tiles — 46 or 92
+// CTAs instead of 23 or 46, a nine-deep operand ring, one epilogue chunk (one 200-token state 0.538 -> 0.507 ms).
+// Beyond that the doubled CTA count saturates L2 (512 tokens: 0.87 vs 0.75 ms) and the 64-wide tiles stay; they
+// write their RMSNorm partial sums per 32-column chunk, so the next kernel reads the same n_parts_lat partials
+// either way and a state's embedding does not depend on what it was batched with.
+constexpr int kLatResBlockN = 32;
+constexpr int kLatResStages = 9;
+constexpr int kLatResMaxTokens = 2 * kBlockM;
 constexpr int kLatStages = 8;
 
 int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, const void* next_weights,
@@ -322,7 +330,11 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 3);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
-    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+    if (T <= kLatResMaxTokens) {
+      RPX_TRY((launch_gemm<kLatResBlockN, EpiResidual, false, kLatResStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+    } else {
+      RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+    }
   }
   {
     Prof p(e, st, 4);
@@ -338,7 +350,11 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 5);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
-    RPX_TRY((launch_gemm<kLatBlockN, EpiResidual, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+    if (T <= kLatResMaxTokens) {
+      RPX_TRY((launch_gemm<kLatResBlockN, EpiResidual, false, kLatResStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+    } else {
+      RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+    }
   }
   return RPX_OK;
 }
@@ -405,8 +421,11 @@ int forward(rpx_encoder* e, const Workspace& ws, int T, int S, int max_len, void
   }
   {
     Prof p(e, st, 6);
+    // latency path: per-group partial rows go where the (now dead) FFN activations were — T rows of d_ff
+    // bf16 hold T rows of d_model fp32 when d_ff >= 2 d_model (else the single-kernel pool runs)
+    float* scratch = latency && (size_t)F * 2 >= (size_t)D * 4 ? reinterpret_cast<float*>(ws.ffn) : nullptr;
     RPX_TRY(launch_pool_normalize(ws.h32, ws.ssA, T, P, e->final_ln, ws.cu_tokens, d_out, out_dtype, S, D,
-                                  c.ln_eps, st, latency));
+                                  c.ln_eps, st, scratch, max_len));
   }
   return RPX_OK;
 }
@@ -441,7 +460,7 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
   e->cfg = *cfg;
   e->inner = inner;
   e->n_parts = ceil_div(D, kBlockN) * (EpiResidual::kWarps / 4);
-  e->n_parts_lat = ceil_div(D, kLatBlockN) * (EpiResidual::kWarps / 4);
+  e->n_parts_lat = ceil_div(D, kLatResBlockN) * (EpiResidual::kWarps / 4);
   auto fail = [&](int code) {
     delete e;
     return code;

@@ -345,17 +345,17 @@ struct RowScale {
   __device__ float get(int m) const {
     if (ss_parts == nullptr) return 1.0f;
     float s = 0.f;
-    // loads in batches of 8 (independent, all in flight together), additions in part order: the latency
-    // path has 23 parts per row and paid one L2 round trip per part with a plain loop
-    int p = 0;
-    for (; p + 8 <= n_parts; p += 8) {
-      float v[8];
+    // loads in batches of 24 (independent, all in flight together), additions in part order: the latency
+    // path has 46 parts per row and would pay one L2 round trip per part with a plain loop
+    constexpr int kBatch = 24;
+    for (int p = 0; p < n_parts; p += kBatch) {
+      float v[kBatch];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ss_parts[(size_t)(p + j) * part_stride + m];
+      for (int j = 0; j < kBatch; ++j) v[j] = p + j < n_parts ? ss_parts[(size_t)(p + j) * part_stride + m] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[j];
+      for (int j = 0; j < kBatch; ++j)
+        if (p + j < n_parts) s += v[j];
     }
-    for (; p < n_parts; ++p) s += ss_parts[(size_t)p * part_stride + m];
     return rsqrtf(s * inv_dim + eps);
   }
 };
@@ -447,21 +447,26 @@ struct EpiStoreBF16 {
 // and dropped: an L2 prefetch of the next tile's residual rows one tile ahead — the lines
 // were evicted again before use, 6.0 GB read per launch against 3.4 GB algorithmic — and L2
 // eviction-priority hints on the residual loads / stores, 0 %.)
-struct EpiResidual {
-  struct Params {
-    float* h32;
-    __nv_bfloat16* h16;
-    int ld;
-    float* ss_out;  // [tiles_n * kWarps / 4][ss_stride]
-    int ss_stride;
-  };
+// CHUNK_SS: one partial sum per 32-column chunk instead of one per tile (ss_out is then indexed by the chunk's
+// position in the row, [N / 32][ss_stride]) — the latency path uses 32- or 64-wide tiles depending on the token
+// count and must hand the next RMSNorm the same partial sums either way.
+struct EpiResidualParams {
+  float* h32;
+  __nv_bfloat16* h16;
+  int ld;
+  float* ss_out;  // [tiles_n * kWarps / 4][ss_stride]
+  int ss_stride;
+};
+template <bool CHUNK_SS>
+struct EpiResidualT {
+  using Params = EpiResidualParams;
   static constexpr int kWarps = RPX_EPI_WARPS;
   static constexpr size_t kSmemBytes = kWarps * 32 * 32 * sizeof(float);  // one 32x32 tile per warp
   Params p;
   float4* stg;  // this warp's staging tile: row r = 8 float4, stored at slot (j ^ (r & 7))
   int lane, grp;
   float4 h[8];  // residual values of the chunk in flight (loaded one chunk ahead)
-  __device__ EpiResidual(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
+  __device__ EpiResidualT(const Params& p_, uint8_t* smem_extra, int row, int part) : p(p_) {
     lane = row & 31;
     grp = row >> 5;
     stg = reinterpret_cast<float4*>(smem_extra) + (part * 4 + grp) * 32 * 8;
@@ -525,20 +530,29 @@ struct EpiResidual {
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) h[i] = hn[i];
+      if (CHUNK_SS) {
+        write_ss(t, ss, row_base, sub, (t.n0 + c) >> 5);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss[i] = 0.f;
+      }
     }
-    // a row's partial sums sit in the 8 lanes that share `sub`
+    if (!CHUNK_SS) write_ss(t, ss, row_base, sub, t.n_blk * t.split + t.part);
+  }
+  // a row's partial sums sit in the 8 lanes that share `sub`
+  __device__ __forceinline__ void write_ss(const TileCtx& t, float (&ss)[8], int row_base, int sub, int part_idx) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
-      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
-      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 4);
+      float v = ss[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
       const int m = row_base + sub + 4 * i;
-      if ((lane & 7) == 0 && m < t.M)
-        p.ss_out[(size_t)(t.n_blk * t.split + t.part) * p.ss_stride + m] = ss[i];
+      if ((lane & 7) == 0 && m < t.M) p.ss_out[(size_t)part_idx * p.ss_stride + m] = v;
     }
   }
   __device__ void finish() {}
 };
+using EpiResidual = EpiResidualT<false>;
 
 // The same residual update with the data movement handed to the TMA engine (2-CTA kernel only).
 //

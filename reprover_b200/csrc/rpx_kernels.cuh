@@ -32,7 +32,7 @@ int launch_embed(const int32_t* ids, const float* table, float* h32, __nv_bfloat
 //   out[s] = normalize( (1/len_s) * sum_t  w .* h32[t] * rs[t] )
 int launch_pool_normalize(const float* h32, const float* ss, int ss_stride, int n_parts, const float* ln_w,
                           const int32_t* cu_tokens, void* out, int out_dtype, int n_seqs, int d_model,
-                          float eps, cudaStream_t stream, bool wide = false);
+                          float eps, cudaStream_t stream, float* group_scratch = nullptr, int max_len = 0);
 
 // Weight packing (rpx_encoder_create): dst[n, k] = bf16(src[n, k] * scale[k]) (scale may be null),
 // rows written at dst_row0 + (n / blk) * blk_stride + (n % blk)  (FFN interleave when blk_stride != blk).
