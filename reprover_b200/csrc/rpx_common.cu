@@ -55,7 +55,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 resolve_encode() {
 }
 
 // cuTensorMapEncodeTiled costs a driver call per map; a single-state encode issues ~100 of them for the
-// same few dozen (pointer, shape) combinations call after call.  Small per-thread direct-mapped cache.
+// same few dozen (pointer, shape) combinations call after call.  Small per-thread 4-way set-associative cache.
 namespace {
 struct TmapKey {
   const void* ptr;
@@ -72,22 +72,38 @@ struct TmapSlot {
   bool valid = false;
   alignas(64) CUtensorMap map;
 };
-constexpr int kTmapSlots = 512;
+constexpr int kTmapSlots = 512, kTmapWays = 4;   // 128 sets x 4 ways
 thread_local TmapSlot g_tmaps[kTmapSlots];
-inline TmapSlot& tmap_slot(const TmapKey& k) {
+thread_local uint8_t g_tmap_next[kTmapSlots / kTmapWays];  // round-robin victim of each set
+inline TmapSlot* tmap_set(const TmapKey& k) {
   uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
   h ^= (k.rows * 0xC2B2AE3D27D4EB4Full) ^ (k.cols << 17) ^ (k.ld << 29) ^ ((uint64_t)k.box_rows << 41) ^
        ((uint64_t)k.box_cols << 49) ^ ((uint64_t)k.elem << 55) ^ ((uint64_t)k.swizzle << 58);
   h ^= h >> 29;
-  return g_tmaps[h % kTmapSlots];
+  return g_tmaps + (h % (kTmapSlots / kTmapWays)) * kTmapWays;
+}
+// The slot holding `k` (hit = true), or the slot to fill (an empty way, else the set's round-robin victim).
+inline TmapSlot& tmap_slot(const TmapKey& k, bool* hit) {
+  TmapSlot* set = tmap_set(k);
+  *hit = true;
+  for (int w = 0; w < kTmapWays; ++w)
+    if (set[w].valid && set[w].key == k) return set[w];
+  *hit = false;
+  for (int w = 0; w < kTmapWays; ++w)
+    if (!set[w].valid) return set[w];
+  uint8_t& nxt = g_tmap_next[(set - g_tmaps) / kTmapWays];
+  TmapSlot& v = set[nxt];
+  nxt = (uint8_t)((nxt + 1) % kTmapWays);
+  return v;
 }
 }  // namespace
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows) {
   const TmapKey key{gptr, rows, cols, ld_elems, 64u, box_rows, 2, 128};
-  TmapSlot& slot = tmap_slot(key);
-  if (slot.valid && slot.key == key) {
+  bool hit;
+  TmapSlot& slot = tmap_slot(key, &hit);
+  if (hit) {
     *out = slot.map;
     return RPX_OK;
   }
@@ -122,8 +138,9 @@ int make_tmap_bf16_2d_uncached(CUtensorMap* out, const void* gptr, uint64_t rows
 int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   const TmapKey key{gptr, rows, cols, ld_elems, box_cols, box_rows, elem_bytes + 16, swizzle_bytes};
-  TmapSlot& slot = tmap_slot(key);
-  if (slot.valid && slot.key == key) {
+  bool hit;
+  TmapSlot& slot = tmap_slot(key, &hit);
+  if (hit) {
     *out = slot.map;
     return RPX_OK;
   }
