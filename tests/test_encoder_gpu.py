@@ -189,6 +189,29 @@ def test_latency_path_matches_oracle_and_throughput_path(rpx_lib, cuda_device, n
     assert max_abs <= EMB_MAX_ABS and min_cos >= EMB_MIN_COS, (max_abs, min_cos)
 
 
+def test_latency_path_batch_equals_single(rpx_lib, cuda_device):
+    """A state's embedding on the latency path does not depend on what it is batched with, although the tile
+    shapes do (32- vs 64-wide residual tiles at 256 tokens, 32 vs 64 hidden units per FFN-up tile at 128): the
+    RMSNorm partial sums, the attention and the pooling are grouped per sequence, not per call."""
+    cfg = dict(synth.BYT5_SMALL)
+    cfg["num_layers"] = 3
+    eng = T5EncoderEngine(cfg, synth.random_t5_state_dict(cfg, seed=6), cuda_device)
+    eng.set_latency_tokens(4096)
+    data, offsets = synth.synth_states(7, seed=31, min_len=5, max_len=250)
+    together = eng.encode_bytes(data, offsets, 2048, out_dtype=torch.float32)      # ~900 tokens in one call
+    strs = synth.split_strings(data, offsets)
+    for i, sbytes in enumerate(strs):
+        alone = eng.encode_bytes(np.frombuffer(sbytes, dtype=np.uint8), np.array([0, len(sbytes)], dtype=np.int64), 2048,
+                                 out_dtype=torch.float32)
+        assert torch.equal(alone[0], together[i]), (i, len(sbytes))
+    pair = eng.encode_bytes(*synth.synth_states(2, seed=32, min_len=100, max_len=120), 2048, out_dtype=torch.float32)
+    d2, o2 = synth.synth_states(2, seed=32, min_len=100, max_len=120)
+    for i, sbytes in enumerate(synth.split_strings(d2, o2)):
+        alone = eng.encode_bytes(np.frombuffer(sbytes, dtype=np.uint8), np.array([0, len(sbytes)], dtype=np.int64), 2048,
+                                 out_dtype=torch.float32)
+        assert torch.equal(alone[0], pair[i])
+
+
 def test_many_short_sequences_and_chunking(rpx_lib, cuda_device, tiny):
     """Hundreds of sequences split over several engine calls (token-budget chunking) == one call."""
     cfg, sd = tiny
