@@ -141,7 +141,7 @@ struct rpx_encoder {
   rpx_t5_config cfg;
   int inner = 0;
   int n_parts = 0;      // RMSNorm partial sums per row on the throughput path: one per 256-wide n-tile
-  int n_parts_lat = 0;  // ... on the latency path: one per 32-wide n-tile
+  int n_parts_lat = 0;  // ... on the latency path: one per 32-column chunk
   int latency_tokens = 0;  // calls with at most this many packed tokens take the latency path (0: never)
   size_t layer_bytes = 0;  // packed weights of one layer (qkv | o | wi | wo, contiguous from LayerW::qkv)
   const float* emb = nullptr;
@@ -300,13 +300,14 @@ struct Prof {
 // BASELINE config-5 rows, two runs each).
 constexpr int kPdlMaxTokens = 16384;
 constexpr int kLatBlockN = 64;
-// The two residual GEMMs of the latency path (O-proj, FFN down) up to 256 tokens: 32-wide tiles — 46 or 92
-// CTAs instead of 23 or 46, a nine-deep operand ring, one epilogue chunk (one 200-token state 0.538 -> 0.507 ms).
-// Beyond that the doubled CTA count saturates L2 (512 tokens: 0.87 vs 0.75 ms) and the 64-wide tiles stay; they
-// write their RMSNorm partial sums per 32-column chunk, so the next kernel reads the same n_parts_lat partials
-// either way and a state's embedding does not depend on what it was batched with.
-constexpr int kLatResBlockN = 32;
-constexpr int kLatResStages = 9;
+// Up to 256 tokens the QKV projection and the two residual GEMMs (O-proj, FFN down) of the latency path run on
+// 64-ROW tiles (tcgen05.mma M = 64): a narrow GEMM's time is the number of k-blocks times the round trip of
+// its operand ring divided by the ring depth, and a 64 x 64 tile's stage is 16 KB instead of 24 KB — twelve
+// stages instead of eight, and twice the CTAs (72 / 92 for a 200-token state).  Beyond 256 tokens the doubled
+// CTA count saturates L2 and the 128-row tiles stay.  Both residual variants write their RMSNorm partial sums
+// per 32-column chunk (n_parts_lat of them), so a state's embedding does not depend on what it was batched with.
+constexpr int kLatSmallM = 64;
+constexpr int kLatSmallStages = 12;
 constexpr int kLatResMaxTokens = 2 * kBlockM;
 constexpr int kLatStages = 8;
 
@@ -318,9 +319,16 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 1);
     EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
-    // the QKV projection occupies 18 x ceil(T/128) SMs: the rest of the GPU fetches the next layer's weights
-    RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatStages>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st, 0,
-                                                                       next_weights, next_bytes)));
+    // the QKV projection occupies 18 x ceil(T/64) (or 18 x ceil(T/128)) SMs: the rest of the GPU fetches the
+    // next layer's weights into L2
+    if (T <= kLatResMaxTokens) {
+      RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatSmallStages, false, kLatSmallM>(ws.h16, D, w.qkv, D, T, 3 * inner,
+                                                                                                 D, ep, st, 0, next_weights,
+                                                                                                 next_bytes)));
+    } else {
+      RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatStages>(ws.h16, D, w.qkv, D, T, 3 * inner, D, ep, st, 0,
+                                                                         next_weights, next_bytes)));
+    }
   }
   {
     Prof p(e, st, 2);
@@ -331,7 +339,8 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
     Prof p(e, st, 3);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
     if (T <= kLatResMaxTokens) {
-      RPX_TRY((launch_gemm<kLatResBlockN, EpiResidual, false, kLatResStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
+      RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatSmallStages, false, kLatSmallM>(ws.attn, inner, w.o, inner, T,
+                                                                                                       D, inner, ep, st)));
     } else {
       RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatStages>(ws.attn, inner, w.o, inner, T, D, inner, ep, st)));
     }
@@ -351,7 +360,8 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
     Prof p(e, st, 5);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
     if (T <= kLatResMaxTokens) {
-      RPX_TRY((launch_gemm<kLatResBlockN, EpiResidual, false, kLatResStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
+      RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatSmallStages, false, kLatSmallM>(ws.ffn, F, w.wo, F, T, D, F,
+                                                                                                       ep, st)));
     } else {
       RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatStages>(ws.ffn, F, w.wo, F, T, D, F, ep, st)));
     }
@@ -460,7 +470,7 @@ int rpx_encoder_create(const rpx_t5_config* cfg, const rpx_t5_weights* w, void* 
   e->cfg = *cfg;
   e->inner = inner;
   e->n_parts = ceil_div(D, kBlockN) * (EpiResidual::kWarps / 4);
-  e->n_parts_lat = ceil_div(D, kLatResBlockN) * (EpiResidual::kWarps / 4);
+  e->n_parts_lat = ceil_div(D, 32) * (EpiResidual::kWarps / 4);  // one per 32-column chunk
   auto fail = [&](int code) {
     delete e;
     return code;

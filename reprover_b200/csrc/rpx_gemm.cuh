@@ -42,9 +42,11 @@ constexpr int kEpiWarp0 = 2;  // first epilogue warp
 template <class Epi>
 constexpr int gemm_threads() { return 64 + 32 * Epi::kWarps; }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int BM = kBlockM>
 struct GemmCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static_assert(BM == 64 || BM == 128, "UMMA M of a 1-CTA tile: 64 or 128");
+  static_assert(2 * STAGES + 4 <= 30, "barrier block holds at most 13 stages");
+  static constexpr int kABytes = BM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
@@ -87,6 +89,7 @@ struct TileCtx {
   int next_m0, next_n0;  // origin of the next tile this CTA will process (next_m0 < 0: none)
   int next_cols;         // its width
   int part, split;       // this warp handles the 32-column chunks with (chunk % split) == part
+  int rows_per_warp;     // tile rows held by one TMEM lane group: 32 (M = 128 tiles) or 16 (M = 64: lanes 16-31 idle)
 };
 
 // Epi must provide:
@@ -105,12 +108,17 @@ struct TileCtx {
 // wi_0 / wi_1 in 128-row blocks (rows [256j, 256j+128) gate, [256j+128, 256j+256) linear, see
 // rpx_encoder.cu), so n-tile t (units u0 = t * BLOCK_N/2) takes rows 256 (u0/128) + u0 % 128 and the same + 128;
 // tmB must then be encoded with a box of BLOCK_N/2 rows.
-template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false, bool SPLIT_B = false>
+//
+// BM = 64 (latency path): 64-row tiles, tcgen05.mma M = 64.  The accumulator then occupies lanes 0-15 of each
+// 32-lane TMEM group (row r of the tile sits in lane 32 (r / 16) + r % 16), so an epilogue warp owns 16 rows and
+// its upper 16 lanes idle.  A CTA takes in half the activation bytes per k-block and the ring holds more
+// stages — what a narrow GEMM's time is made of (see rpx_encoder.cu).
+template <int BLOCK_N, int STAGES, class Epi, bool M_FASTEST = false, bool SPLIT_B = false, int BM = kBlockM>
 __global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int tiles_m, int tiles_n, int n_blk_stride, typename Epi::Params ep,
                L2Prefetch pf) {
-  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  using Cfg = GemmCfg<BLOCK_N, STAGES, BM>;
   if (threadIdx.x == 0) RPX_STAMP(pf, 0);
   if ((int)blockIdx.x >= pf.work_ctas) {
     // Helper CTA (latency path): the GEMM itself keeps only a fraction of the SMs busy, so the launch is
@@ -220,9 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // prefetch of the streamed operand a few k-blocks ahead of its TMA load was also measured:
           // 6-12 % slower at every distance tried, removed.)
           if (M_FASTEST) {
-            tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM, kEvictLast);
+            tma_load_2d_hint(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * BM, kEvictLast);
           } else {
-            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kb * kBlockK, m_blk * BM);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -243,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int n_this = N - n_blk * n_blk_stride * BLOCK_N;
         if (n_this > BLOCK_N) n_this = BLOCK_N;
         n_this = (n_this + 15) & ~15;
-        const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)n_this);
+        const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)n_this);
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -273,17 +281,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue
     const int lane_grp = warp & 3;                            // TMEM lane group this warp may read
-    const int row = lane_grp * 32 + (threadIdx.x & 31);       // row of the tile this thread owns
+    const int lane = threadIdx.x & 31;
+    // row of the tile this thread owns; with 64-row tiles lanes 16-31 of a group hold nothing: their row lies
+    // beyond every matrix, so the functors' `m < M` tests switch them off
+    const int row = BM == kBlockM ? lane_grp * 32 + lane : (lane < 16 ? lane_grp * 16 + lane : (1 << 28));
     const int part = (warp - kEpiWarp0) >> 2;                 // which share of the columns (0 when 4 warps)
     pdl_wait();  // the epilogue reads (row scales, residual stream) and overwrites the predecessor's outputs
-    Epi epi(ep, smem_extra, row, part);
+    Epi epi(ep, smem_extra, lane_grp * 32 + lane, part);      // (the functor's staging is per TMEM lane)
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += pf.work_ctas) {
       TileCtx t;
       t.n_blk = M_FASTEST ? tile / tiles_m : tile % tiles_n;
       t.m_blk = M_FASTEST ? tile % tiles_m : tile / tiles_n;
-      t.m0 = t.m_blk * kBlockM;
+      t.m0 = t.m_blk * BM;
+      t.rows_per_warp = BM / 4;
       t.n0 = t.n_blk * n_blk_stride * BLOCK_N;  // (n_blk stays the logical tile index)
       int n_this = N - t.n0;
       if (n_this > BLOCK_N) n_this = BLOCK_N;
@@ -297,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const int nt = tile + pf.work_ctas;
         if (nt < num_tiles) {
-          t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * kBlockM;
+          t.next_m0 = (M_FASTEST ? nt % tiles_m : nt / tiles_n) * BM;
           t.next_n0 = (M_FASTEST ? nt / tiles_m : nt % tiles_n) * BLOCK_N;
           t.next_cols = N - t.next_n0 < BLOCK_N ? N - t.next_n0 : BLOCK_N;
         } else {
@@ -476,8 +488,8 @@ struct EpiResidualT {
     const size_t col = (size_t)t.n0 + c + col4;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int m = row_base + sub + 4 * i;
-      if (m < t.M) hh[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
+      const int r = sub + 4 * i, m = row_base + r;
+      if (r < t.rows_per_warp && m < t.M) hh[i] = *reinterpret_cast<const float4*>(p.h32 + (size_t)m * p.ld + col);
       else hh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -485,13 +497,13 @@ struct EpiResidualT {
   // the tile are still running (on the latency path that L2 round trip was a third of the epilogue)
   __device__ void before_wait(const TileCtx& t) {
     const int c = 32 * t.part;
-    if (c < t.n_cols) load_chunk(t, c, t.m0 + grp * 32, lane >> 3, (lane & 7) * 4, h);
+    if (c < t.n_cols) load_chunk(t, c, t.m0 + grp * t.rows_per_warp, lane >> 3, (lane & 7) * 4, h);
   }
   __device__ void tile(const TileCtx& t) {
     const int sub = lane >> 3;        // row within a group of 4
     const int j4 = lane & 7;          // which float4 of the 32-column chunk
     const int col4 = j4 * 4;
-    const int row_base = t.m0 + grp * 32;
+    const int row_base = t.m0 + grp * t.rows_per_warp;
     const int step = 32 * t.split;
     float ss[8];
 #pragma unroll
@@ -521,7 +533,7 @@ struct EpiResidualT {
         h[i].z += a.z;
         h[i].w += a.w;
         ss[i] += h[i].x * h[i].x + h[i].y * h[i].y + h[i].z * h[i].z + h[i].w * h[i].w;
-        if (m < t.M) {
+        if (r < t.rows_per_warp && m < t.M) {
           *reinterpret_cast<float4*>(p.h32 + (size_t)m * p.ld + col) = h[i];
           *reinterpret_cast<uint2*>(p.h16 + (size_t)m * p.ld + col) =
               make_uint2(pack_bf16x2(h[i].x, h[i].y), pack_bf16x2(h[i].z, h[i].w));
@@ -546,8 +558,8 @@ struct EpiResidualT {
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      const int m = row_base + sub + 4 * i;
-      if ((lane & 7) == 0 && m < t.M) p.ss_out[(size_t)part_idx * p.ss_stride + m] = v;
+      const int r = sub + 4 * i, m = row_base + r;
+      if ((lane & 7) == 0 && r < t.rows_per_warp && m < t.M) p.ss_out[(size_t)part_idx * p.ss_stride + m] = v;
     }
   }
   __device__ void finish() {}

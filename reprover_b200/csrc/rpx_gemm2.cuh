@@ -268,6 +268,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       t.m0 = t.m_blk * kPairM + (int)rank * kBlockM;
       t.n_cols = n_this < N - t.n0 ? n_this : ((N - t.n0 + 31) & ~31);
       t.row = row;
+      t.rows_per_warp = 32;
       t.part = part;
       t.split = Epi::kWarps / 4;
       t.M = M;

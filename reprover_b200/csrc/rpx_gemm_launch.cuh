@@ -12,26 +12,27 @@ constexpr int kGemmStages = 4;
 // `grid_limit` caps the persistent grid (0 = one CTA per SM).
 // M_FASTEST kernels take the grid size verbatim from `grid_limit` (the caller sizes it as a
 // multiple of tiles_m) and accept any N (the epilogue masks the ragged tail).
-template <int BLOCK_N, class Epi, bool M_FASTEST = false, int STAGES = kGemmStages, bool SPLIT_B = false>
+template <int BLOCK_N, class Epi, bool M_FASTEST = false, int STAGES = kGemmStages, bool SPLIT_B = false, int BM = kBlockM>
 int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 const typename Epi::Params& ep, cudaStream_t stream, int grid_limit = 0, const void* prefetch_ptr = nullptr,
                 size_t prefetch_bytes = 0) {
-  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  using Cfg = GemmCfg<BLOCK_N, STAGES, BM>;
+  static_assert(BM == kBlockM || (!M_FASTEST && Epi::kWarps == 4), "64-row tiles: encoder epilogues with one warp per lane group");
   RPX_REQUIRE(M > 0 && N > 0 && K > 0, RPX_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RPX_REQUIRE(K % kBlockK == 0, RPX_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, kBlockK);
   RPX_REQUIRE(M_FASTEST || N % 32 == 0, RPX_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 32", N);
   DeviceInfo dev;
   RPX_TRY(get_device_info(&dev));
   CUtensorMap tmA, tmB;
-  RPX_TRY(make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockM));
+  RPX_TRY(make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM));
   RPX_TRY(make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, SPLIT_B ? BLOCK_N / 2 : BLOCK_N));
   RPX_REQUIRE(!SPLIT_B || N % BLOCK_N == 0, RPX_ERR_UNSUPPORTED, "gemm: split-B tiles need N %% %d == 0", BLOCK_N);
-  const int tiles_m = ceil_div(M, kBlockM);
+  const int tiles_m = ceil_div(M, BM);
   const int tiles_n = ceil_div(N, BLOCK_N);
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   RPX_REQUIRE(smem <= dev.smem_optin, RPX_ERR_UNSUPPORTED, "gemm: needs %zu B smem, device allows %zu",
               smem, dev.smem_optin);
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, Epi, M_FASTEST, SPLIT_B>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, Epi, M_FASTEST, SPLIT_B, BM>;
   static thread_local int configured_dev = -1;  // per-instantiation, per-thread
   if (configured_dev != dev.device) {
     RPX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
