@@ -386,26 +386,29 @@ t5_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-shot variant for short sequences (<= 256 keys) on the encoder's latency path.  One proof state
-// is a handful of (128-query tile, head) pairs — 12 CTAs on a 148-SM machine — and in each of them one warp
-// walks the whole key range of its 32 rows twice (row maximum, then exponentials): that walk, not the
-// tensor core, is the critical path.  Here a CTA takes 32 QUERIES and all four softmax warps work on them:
+// Latency-path variant (one or a few proof states per call, <= 1024 keys).  One proof state is a handful of
+// (128-query tile, head) pairs — 12 CTAs on a 148-SM machine for 225 tokens — and in each of them one warp
+// walks the whole key range of its 32 rows in 64-key steps: that walk, not the tensor core, is the critical
+// path.  Here a CTA takes 32 QUERIES and all four softmax warps work on them, 256 keys at a time:
 //   * the 32 query rows are loaded FOUR times, into row groups 0-31 / 32-63 / 64-95 / 96-127 of the Q tile,
-//     so S[128 x keys] = Q K^T (one group of N <= 256 MMAs, the whole key range at once) holds the same 32
-//     score rows in all four TMEM lane groups — a warp can only read its own lane group;
-//   * warp w handles the 32-key chunks w and w + 4 of those rows: maximum and sum are combined across
-//     the warps through shared memory (two named-barrier syncs), each warp writes its chunks of P;
-//   * O = P V from one run of MMAs; only rows 0-31 of P / O mean anything, warp 0 stores them.
-// No running maximum, no O rescale.  Four times the CTAs (48 for a 225-token state), a quarter of the
-// serial softmax work in each.
-constexpr int kShortKeys = 256;
+//     so S[128 x 256] = Q K^T (one group of N <= 256 MMAs per key block) holds the same 32 score rows in all
+//     four TMEM lane groups — a warp can only read its own lane group;
+//   * warp w handles the 32-key chunks w and w + 4 of a block: block maximum and row sums are combined
+//     across the warps through shared memory, each warp writes its chunks of P;
+//   * O += P V from one run of MMAs per block; only rows 0-31 of P / O mean anything, warp 0 rescales them
+//     between blocks (exact running maximum, at most three rescales) and stores them.
+// A state of <= 256 tokens is ONE block: no running maximum, no rescale.  Four times the CTAs of the streaming
+// kernel (48 for a 225-token state), a quarter of the serial softmax work in each, a quarter of the steps.
+constexpr int kShortKeys = 256;                                      // keys per block
+constexpr int kShortMaxKeys = 1024;                                  // longest sequence this kernel takes
 constexpr int kShortQ = 32;                                          // queries per CTA
+constexpr int kShortKVBytes = kShortKeys * 128;                      // one K or V block [256 keys][64 bf16]
 constexpr int kShortOffQ = 0;
-constexpr int kShortOffK = kQBytes;                                  // [256 keys][64 bf16]
-constexpr int kShortOffV = kQBytes + kShortKeys * 128;
-constexpr int kShortOffP = kQBytes + 2 * kShortKeys * 128;           // 4 tiles of [128 rows][64 keys]
-constexpr int kShortOffRed = kShortOffP + 4 * kQBytes;               // max[4][32], sum[4][32] floats
-constexpr int kShortOffBias = kShortOffRed + 2 * 4 * 32 * 4;
+constexpr int kShortOffK = kQBytes;                                  // two K blocks
+constexpr int kShortOffV = kShortOffK + 2 * kShortKVBytes;           // two V blocks
+constexpr int kShortOffP = kShortOffV + 2 * kShortKVBytes;           // 4 tiles of [128 rows][64 keys]
+constexpr int kShortOffRed = kShortOffP + 4 * kQBytes;               // max[2][4][32], sum[4][32] floats
+constexpr int kShortOffBias = kShortOffRed + 3 * 4 * 32 * 4;
 
 RPX_DEVICE void softmax_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -416,31 +419,30 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   pdl_launch_dependents();   // (prologue ahead of the predecessor's end: see t5_attention_tc_kernel)
   const int t0 = cu_seqlens[seq];
-  const int len = cu_seqlens[seq + 1] - t0;   // <= kShortKeys (checked by the launcher through max_len)
+  const int len = cu_seqlens[seq + 1] - t0;   // <= kShortMaxKeys (checked by the launcher through max_len)
   const int q0 = qt * kShortQ;
   if (q0 >= len) return;  // whole CTA
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
-  float* sMax = reinterpret_cast<float*>(smem + kShortOffRed);   // [4][32]
-  float* sSum = sMax + 4 * 32;                                   // [4][32]
+  float* sMax = reinterpret_cast<float*>(smem + kShortOffRed);   // [2][4][32] (alternating by block)
+  float* sSum = sMax + 2 * 4 * 32;                               // [4][32]
   float* sBias = reinterpret_cast<float*>(smem + kShortOffBias);
   const int lut_w = 2 * R + 1;
   const int bstride = bias_copy_stride(R);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kShortOffBias + 4 * bstride * 4);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_p = bars + 4;
-  uint64_t* bar_o = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_k = bars + 1;   // [2]
+  uint64_t* bar_v = bars + 3;   // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_p = bars + 6;
+  uint64_t* bar_o = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = n_heads * kHD;
-  const int n_box = (len + kKT - 1) / kKT;            // 64-key TMA boxes of K and of V
-  const int n_mma = (len + 15) & ~15;                 // key extent of the MMAs
+  const int n_blocks = (len + kShortKeys - 1) / kShortKeys;
 
   if (threadIdx.x < 128)
     for (int i = threadIdx.x; i < 4 * bstride; i += 128) {
@@ -450,8 +452,10 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   if (warp == 4) {
     if (elect_one()) {
       mbar_init(bar_q, 1);
-      mbar_init(bar_k, 1);
-      mbar_init(bar_v, 1);
+      mbar_init(&bar_k[0], 1);
+      mbar_init(&bar_k[1], 1);
+      mbar_init(&bar_v[0], 1);
+      mbar_init(&bar_v[1], 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
@@ -469,99 +473,144 @@ t5_attention_short_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   if (warp == 4) {
     if (elect_one()) {
       const int kcol = inner + head * kHD, vcol = 2 * inner + head * kHD;
+      auto load_kv = [&](int b) {   // key block b into buffer b & 1
+        const int keys = min(kShortKeys, len - b * kShortKeys);
+        const int n_box = (keys + kKT - 1) / kKT;   // 64-key TMA boxes
+        uint8_t* kdst = smem + kShortOffK + (b & 1) * kShortKVBytes;
+        uint8_t* vdst = smem + kShortOffV + (b & 1) * kShortKVBytes;
+        mbar_arrive_expect_tx(&bar_k[b & 1], (uint32_t)(n_box * kKVBytes));
+        for (int i = 0; i < n_box; ++i) tma_load_2d(kdst + i * kKVBytes, &tm_kv, &bar_k[b & 1], kcol, t0 + b * kShortKeys + i * kKT);
+        mbar_arrive_expect_tx(&bar_v[b & 1], (uint32_t)(n_box * kKVBytes));
+        for (int i = 0; i < n_box; ++i) tma_load_2d(vdst + i * kKVBytes, &tm_kv, &bar_v[b & 1], vcol, t0 + b * kShortKeys + i * kKT);
+      };
+      const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);            // O[128 x 64] += P[128 x 16] V[16 x 64]
+      const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffQ));
+      auto issue_s = [&](int b) {   // S[128 x n] = Q[128 x 64] K_b[n x 64]^T
+        const int keys = min(kShortKeys, len - b * kShortKeys);
+        const uint32_t idesc_s = make_idesc_bf16(kQT, (uint32_t)((keys + 15) & ~15));
+        const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffK + (b & 1) * kShortKVBytes));
+        mbar_wait<0>(&bar_k[b & 1], (b >> 1) & 1, 32);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      };
       pdl_wait();
       mbar_arrive_expect_tx(bar_q, kQBytes);
       for (int g = 0; g < 4; ++g)   // the same 32 query rows into every row group of the tile
         tma_load_2d(smem + kShortOffQ + g * kShortQ * 128, &tm_q, bar_q, head * kHD, t0 + q0);
-      mbar_arrive_expect_tx(bar_k, (uint32_t)(n_box * kKVBytes));
-      for (int b = 0; b < n_box; ++b) tma_load_2d(smem + kShortOffK + b * kKVBytes, &tm_kv, bar_k, kcol, t0 + b * kKT);
-      mbar_arrive_expect_tx(bar_v, (uint32_t)(n_box * kKVBytes));
-      for (int b = 0; b < n_box; ++b) tma_load_2d(smem + kShortOffV + b * kKVBytes, &tm_kv, bar_v, vcol, t0 + b * kKT);
-
-      const uint32_t idesc_s = make_idesc_bf16(kQT, (uint32_t)n_mma);   // S[128 x n] = Q[128 x 64] K[n x 64]^T
-      const uint32_t idesc_o = make_idesc_bf16_bmn(kQT, kHD);            // O[128 x 64] += P[128 x 16] V[16 x 64]
-      const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffQ));
-      const uint64_t k_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffK));
-      const uint32_t v_base = smem_u32(smem + kShortOffV);
+      load_kv(0);
+      if (n_blocks > 1) load_kv(1);
       mbar_wait<0>(bar_q, 0, 31);
-      mbar_wait<0>(bar_k, 0, 32);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < kHD / 16; ++k) umma_bf16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-      umma_commit(bar_s);
-      mbar_wait<0>(bar_p, 0, 33);
-      mbar_wait<0>(bar_v, 0, 34);
-      tc_fence_after();
-      for (int j = 0; j < n_mma / 16; ++j) {
-        // A = P tile j/4 (K-major, 32 B per 16 keys); B = V (MN-major): 16 keys = two 8-row groups = 2048 B
-        const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffP + (j >> 2) * kQBytes)) + 2 * (j & 3);
-        const uint64_t v_desc = make_smem_desc_mnmajor_sw128(v_base + j * 2048);
-        umma_bf16_ss(tmem_O, p_desc, v_desc, idesc_o, j != 0);
+      issue_s(0);
+      for (int b = 0; b < n_blocks; ++b) {
+        const int keys = min(kShortKeys, len - b * kShortKeys);
+        const int n_mma = (keys + 15) & ~15;
+        const uint32_t v_base = smem_u32(smem + kShortOffV + (b & 1) * kShortKVBytes);
+        mbar_wait<0>(bar_p, b & 1, 33);
+        mbar_wait<0>(&bar_v[b & 1], (b >> 1) & 1, 34);
+        tc_fence_after();
+        for (int j = 0; j < n_mma / 16; ++j) {
+          // A = P tile j/4 (K-major, 32 B per 16 keys); B = V (MN-major): 16 keys = two 8-row groups = 2048 B
+          const uint64_t p_desc = make_smem_desc_kmajor_sw128(smem_u32(smem + kShortOffP + (j >> 2) * kQBytes)) + 2 * (j & 3);
+          const uint64_t v_desc = make_smem_desc_mnmajor_sw128(v_base + j * 2048);
+          umma_bf16_ss(tmem_O, p_desc, v_desc, idesc_o, (b | j) != 0);
+        }
+        umma_commit(bar_o);
+        // the next block's scores right behind this block's P V (the softmax warps are done with S: they have
+        // arrived on bar_p); MMAs retire in order, so `bar_s` of block b + 1 also says P V of block b is done
+        if (b + 1 < n_blocks) issue_s(b + 1);
+        if (b + 2 < n_blocks) {   // K / V buffer b & 1 is free once P V of block b has read it
+          mbar_wait<0>(bar_o, b & 1, 37);
+          load_kv(b + 2);
+        }
       }
-      umma_commit(bar_o);
     }
   } else {
     // query row `lane` of the CTA; this warp's copy of its scores sits in TMEM lanes [32 warp, 32 warp + 32)
     const int qpos = q0 + lane;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float kLog2e = 1.4426950408889634f;
-    const int n_chunks = (n_mma + 31) >> 5;   // 32-key chunks that hold keys the MMAs read
-    mbar_wait<0>(bar_s, 0, 35);
-    tc_fence_after();
-    // pass 1: maximum over this warp's chunks, then over the warps
-    float mx = -INFINITY;
-    for (int c = warp; c < n_chunks; c += 4) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
-      tmem_ld_wait();
-      float sc[32];
+    float m_run = -INFINITY, l_run = 0.f;   // l_run: this warp's share of the row sum, relative to m_run
+    for (int b = 0; b < n_blocks; ++b) {
+      const int kb = b * kShortKeys;                               // first key of the block
+      const int keys = min(kShortKeys, len - kb);
+      const int n_chunks = (((keys + 15) & ~15) + 31) >> 5;        // 32-key chunks that hold keys the MMAs read
+      mbar_wait<0>(bar_s, b & 1, 35);   // (also: P V of block b - 1 has retired — P and O may be touched)
+      tc_fence_after();
+      // pass 1: block maximum over this warp's chunks, then over the warps
+      float mx = -INFINITY;
+      for (int c = warp; c < n_chunks; c += 4) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+        tmem_ld_wait();
+        float sc[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
-      add_bias32(sc, sBias, 32 * c - qpos + R, R, bstride);
-      const int lim = len - 32 * c;   // keys of this chunk inside the sequence
+        for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
+        add_bias32(sc, sBias, kb + 32 * c - qpos + R, R, bstride);
+        const int lim = keys - 32 * c;   // keys of this chunk inside the sequence
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < lim ? sc[j] : -INFINITY);
-    }
-    sMax[warp * 32 + lane] = mx;
-    softmax_warps_sync();
-    mx = fmaxf(fmaxf(sMax[lane], sMax[32 + lane]), fmaxf(sMax[64 + lane], sMax[96 + lane]));  // (chunk 0 is never empty)
-    // pass 2: exponentials, row sum, P
-    const float mb = mx * kLog2e;
-    float l0 = 0.f, l1 = 0.f;
-    for (int c = warp; c < n_chunks; c += 4) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
-      tmem_ld_wait();
-      float sc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
-      add_bias32(sc, sBias, 32 * c - qpos + R, R, bstride);
-      const int lim = (qpos < len) ? len - 32 * c : 0;   // rows past the sequence contribute nothing
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float p0 = j < lim ? fast_exp2(fmaf(sc[j], kLog2e, -mb)) : 0.f;
-        const float p1 = j + 1 < lim ? fast_exp2(fmaf(sc[j + 1], kLog2e, -mb)) : 0.f;
-        l0 += p0;
-        l1 += p1;
-        pk[j >> 1] = pack_bf16x2(p0, p1);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < lim ? sc[j] : -INFINITY);
       }
-      // P row `lane` (rows 32-127 of the tiles are never written: their O rows are never read)
-      uint8_t* prow = smem + kShortOffP + (c >> 1) * kQBytes + lane * 128;
-      const int h = c & 1;
+      float* smx = sMax + (b & 1) * 128;
+      smx[warp * 32 + lane] = mx;
+      softmax_warps_sync();
+      mx = fmaxf(fmaxf(smx[lane], smx[32 + lane]), fmaxf(smx[64 + lane], smx[96 + lane]));  // (chunk 0 is never empty)
+      const float m_new = fmaxf(m_run, mx);
+      const float scale = fast_exp2((m_run - m_new) * kLog2e);   // 0 for the first block (m_run = -inf)
+      m_run = m_new;
+      // pass 2: exponentials, row sum, P
+      const float mb = m_new * kLog2e;
+      float l0 = 0.f, l1 = 0.f;
+      for (int c = warp; c < n_chunks; c += 4) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+        tmem_ld_wait();
+        float sc[32];
 #pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int slot = (h * 4 + s4) ^ (lane & 7);
-        *reinterpret_cast<uint4*>(prow + slot * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+        for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
+        add_bias32(sc, sBias, kb + 32 * c - qpos + R, R, bstride);
+        const int lim = (qpos < len) ? keys - 32 * c : 0;   // rows past the sequence contribute nothing
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = j < lim ? fast_exp2(fmaf(sc[j], kLog2e, -mb)) : 0.f;
+          const float p1 = j + 1 < lim ? fast_exp2(fmaf(sc[j + 1], kLog2e, -mb)) : 0.f;
+          l0 += p0;
+          l1 += p1;
+          pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+        // P row `lane` (rows 32-127 of the tiles are never written: their O rows are never read)
+        uint8_t* prow = smem + kShortOffP + (c >> 1) * kQBytes + lane * 128;
+        const int h = c & 1;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int slot = (h * 4 + s4) ^ (lane & 7);
+          *reinterpret_cast<uint4*>(prow + slot * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+        }
       }
+      l_run = l_run * scale + (l0 + l1);
+      // O rows 0-31 (warp 0's lanes) *= exp(m_old - m_new) before P V of this block accumulates onto them
+      if (warp == 0 && b > 0 && !__all_sync(0xffffffffu, scale == 1.f)) {
+#pragma unroll
+        for (int c = 0; c < kHD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_O + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * scale);
+          tmem_st_32x32(tmem_O + c * 32, v);
+        }
+        tmem_st_wait();
+      }
+      if (b + 1 == n_blocks) sSum[warp * 32 + lane] = l_run;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
     }
-    sSum[warp * 32 + lane] = l0 + l1;
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(bar_p);
 
     if (warp == 0) {
-      mbar_wait<0>(bar_o, 0, 36);   // (PV needed every warp's P, so every warp's partial sum is in sSum as well)
+      mbar_wait<0>(bar_o, (n_blocks - 1) & 1, 36);   // (P V needed every warp's P, so every warp's sum is in sSum)
       tc_fence_after();
       const float inv = 1.f / ((sSum[lane] + sSum[32 + lane]) + (sSum[64 + lane] + sSum[96 + lane]));
       __nv_bfloat16* dst = out + (int64_t)(t0 + qpos) * ld_out + head * kHD;
@@ -607,7 +656,7 @@ int launch_t5_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int3
   RPX_TRY(get_device_info(&dev));
   CUtensorMap tm_q, tm_kv;
   RPX_TRY(make_tmap_bf16_2d(&tm_kv, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kKT));
-  if (latency && max_len <= kShortKeys) {
+  if (latency && max_len <= kShortMaxKeys) {
     const size_t smem_short = 1024 + kShortOffBias + (size_t)4 * bias_copy_stride(max_distance) * 4 + 128;
     if (smem_short <= dev.smem_optin) {
       RPX_TRY(make_tmap_bf16_2d(&tm_q, qkv, (uint64_t)n_tokens, (uint64_t)3 * inner, (uint64_t)3 * inner, kShortQ));

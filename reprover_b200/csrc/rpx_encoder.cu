@@ -308,7 +308,10 @@ constexpr int kLatBlockN = 64;
 // per 32-column chunk (n_parts_lat of them), so a state's embedding does not depend on what it was batched with.
 constexpr int kLatSmallM = 64;
 constexpr int kLatSmallStages = 12;
-constexpr int kLatResMaxTokens = 2 * kBlockM;
+#ifndef RPX_LAT_SMALLM_TOKENS
+#define RPX_LAT_SMALLM_TOKENS 256
+#endif
+constexpr int kLatResMaxTokens = RPX_LAT_SMALLM_TOKENS;
 constexpr int kLatStages = 8;
 
 int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, const void* next_weights,
