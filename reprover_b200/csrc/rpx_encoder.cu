@@ -300,16 +300,16 @@ struct Prof {
 // BASELINE config-5 rows, two runs each).
 constexpr int kPdlMaxTokens = 16384;
 constexpr int kLatBlockN = 64;
-// Up to 256 tokens the QKV projection and the two residual GEMMs (O-proj, FFN down) of the latency path run on
+// Up to 384 tokens the QKV projection and the two residual GEMMs (O-proj, FFN down) of the latency path run on
 // 64-ROW tiles (tcgen05.mma M = 64): a narrow GEMM's time is the number of k-blocks times the round trip of
 // its operand ring divided by the ring depth, and a 64 x 64 tile's stage is 16 KB instead of 24 KB — twelve
-// stages instead of eight, and twice the CTAs (72 / 92 for a 200-token state).  Beyond 256 tokens the doubled
-// CTA count saturates L2 and the 128-row tiles stay.  Both residual variants write their RMSNorm partial sums
+// stages instead of eight, and twice the CTAs (72 / 92 for a 200-token state).  Beyond 384 tokens the 64-row
+// tiles no longer fit in one wave (512 tokens: 0.99 vs 0.59 ms) and the 128-row tiles stay.  Both residual variants write their RMSNorm partial sums
 // per 32-column chunk (n_parts_lat of them), so a state's embedding does not depend on what it was batched with.
 constexpr int kLatSmallM = 64;
 constexpr int kLatSmallStages = 12;
 #ifndef RPX_LAT_SMALLM_TOKENS
-#define RPX_LAT_SMALLM_TOKENS 256
+#define RPX_LAT_SMALLM_TOKENS 384   // 6 row tiles x 23 column tiles = 138 CTAs: the most one wave holds
 #endif
 constexpr int kLatResMaxTokens = RPX_LAT_SMALLM_TOKENS;
 constexpr int kLatStages = 8;
