@@ -362,9 +362,31 @@ struct EpiSampleScores {
 // sample key: one pass over the scores, one pass over shared memory, one block scan (the bisection this
 // replaces took 12 block-wide probes: 39 us per 1024 queries against ~5 us).  T is the lower edge of the
 // bin in which the n_res-th best key falls, so stage 1 admits at most that bin's extra keys.
+// The kernel also resets the per-query bookkeeping stage 1 starts from (list counts, final thresholds, the
+// shared gmin / gcnt bound) — three memset launches less per call.
+struct StageOneReset {
+  int32_t* cnt;        // [grid][128]
+  float* thr_out;      // [grid][128]: NaN = "no list here", skipped by stage 2's fmaxf reduction
+  uint32_t* gcnt;      // [tiles_m * 128]
+  uint32_t* gmin;      // [tiles_m * 128]
+  int n_seg, tiles_m;
+};
 constexpr int kThrBins = 1024;
 __global__ void __launch_bounds__(256)
-sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_res, uint32_t* __restrict__ gthr) {
+sample_threshold_kernel(const float* __restrict__ S, int ld, int n_cols, int n_res, uint32_t* __restrict__ gthr,
+                        const StageOneReset rs) {
+  {
+    const int q = blockIdx.x, q_blk = q / kBlockM, row = q % kBlockM;
+    for (int s = threadIdx.x; s < rs.n_seg; s += 256) {
+      const int slot = (q_blk + s * rs.tiles_m) * kBlockM + row;
+      rs.cnt[slot] = 0;
+      rs.thr_out[slot] = __uint_as_float(0xFFFFFFFFu);
+    }
+    if (threadIdx.x == 0) {
+      rs.gcnt[q] = 0u;
+      rs.gmin[q] = 0xFFFFFFFFu;
+    }
+  }
   extern __shared__ __align__(16) uint8_t sm_raw[];
   uint32_t* keys = reinterpret_cast<uint32_t*>(sm_raw);
   __shared__ int hist[kThrBins];
@@ -923,21 +945,23 @@ int run_mma_topk(const TopkCall& c, void* ws, size_t ws_bytes) {
     const int nq_c = nq - q0 < chunk_q ? nq - q0 : chunk_q;
     // (only the last chunk can be smaller; its tiles_m may shrink but the plan's grid stays valid
     //  because we keep tiles_m fixed and let the surplus query blocks be empty)
-    RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + 2 * pl.gthr_bytes, st));  // cnt, gthr, gcnt are adjacent
-    RPX_CUDA_OK(cudaMemsetAsync(gmin, 0xFF, pl.gthr_bytes, st));
-    // lists no stage-1 CTA visits keep count 0 and must not contribute a threshold: 0xFF bytes are a NaN,
-    // which the fmaxf() reduction in stage 2 skips
-    RPX_CUDA_OK(cudaMemsetAsync(thr_out, 0xFF, pl.cnt_bytes, st));
     const uint32_t* mask_c = c.mask ? c.mask + (size_t)q0 * c.mask_stride : nullptr;
     const int64_t tiles_n_all = ceil_div64(n, kSimBlockN);
     if (tiles_n_all >= 4 * (int64_t)pl.sample_tiles) {
-      // stage 0: starting thresholds from a strided sample of the corpus (overwrites gthr)
+      // stage 0: starting thresholds from a strided sample of the corpus (writes gthr, resets the rest)
       const int ld = pl.sample_tiles * kSimBlockN;
       EpiSampleScores::Params sp{sample, ld, mask_c, c.mask_stride, nq_c, (int)n};
       RPX_TRY((launch_sim_epi<EpiSampleScores>(Q + (size_t)q0 * d, nq_c, E, n, d, sp, pl, st, pl.sample_tiles,
                                                 (int)(tiles_n_all / pl.sample_tiles))));
-      sample_threshold_kernel<<<nq_c, 256, (size_t)ld * sizeof(uint32_t), st>>>(sample, ld, ld, pl.n_res, gthr);
+      const StageOneReset rs{cnt, thr_out, gcnt, gmin, n_seg, pl.tiles_m};
+      sample_threshold_kernel<<<nq_c, 256, (size_t)ld * sizeof(uint32_t), st>>>(sample, ld, ld, pl.n_res, gthr, rs);
       RPX_CUDA_OK(cudaGetLastError());
+    } else {
+      // small corpus, no sampling pass: plain resets.  Lists no stage-1 CTA visits keep count 0 and must not
+      // contribute a threshold: 0xFF bytes are a NaN, which the fmaxf() reduction in stage 2 skips
+      RPX_CUDA_OK(cudaMemsetAsync(cnt, 0, pl.cnt_bytes + 2 * pl.gthr_bytes, st));  // cnt, gthr, gcnt are adjacent
+      RPX_CUDA_OK(cudaMemsetAsync(gmin, 0xFF, pl.gthr_bytes, st));
+      RPX_CUDA_OK(cudaMemsetAsync(thr_out, 0xFF, pl.cnt_bytes, st));
     }
     if (n > 0) {
       SimTopkParams ep{cand, cnt, thr_out, gthr, gmin, gcnt, n_seg, rank_r, pl.list_max, mask_c, c.mask_stride, nq_c, (int)n, pl.tiles_m};
