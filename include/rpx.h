@@ -130,12 +130,16 @@ int rpx_encode_ids(rpx_encoder* enc, const int64_t* d_input_ids, const int64_t* 
                    int32_t batch, int32_t seq_len, void* d_out, int32_t out_dtype,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Latency path: encode calls with at most `max_tokens` packed tokens (0 = never, the default) run the
- * layer GEMMs on narrow 1-CTA tiles (128 tokens x 64 columns) that spread a single proof state's work
- * over ~20-110 SMs instead of the 256 x 256 pair tiles that are sized for re-indexing.  This is the
- * shape of the reference's per-state call (`retrieve`, retrieval/model.py:348-357).  Results agree with
- * the throughput path to fp32 rounding of the RMSNorm statistics (not bit for bit), so a caller that needs
- * batch-invariant bits (re-indexing) leaves it off. */
+/* Latency path: encode calls with at most `max_tokens` packed tokens (0 = never, the default) run on
+ * kernels shaped for ONE proof state — the reference's per-state call (`retrieve`,
+ * retrieval/model.py:348-357) — instead of the 256 x 256 pair tiles that are sized for re-indexing: narrow
+ * 1-CTA GEMM tiles (64 or 128 tokens x 64 columns, 128 x 128 for the gated FFN-up) that spread the state's work
+ * over 70-140 SMs, attention on 32-query CTAs whose four softmax warps share the key range, pooling as
+ * per-group partial rows, everything chained by programmatic dependent launch.  Results agree with the
+ * throughput path to a few 1e-4 on unit-norm embeddings (the RMSNorm statistics are summed in another
+ * grouping, which flips the odd bf16 rounding of an intermediate), not bit for bit, so a caller that needs
+ * re-indexing's bits leaves it off; within the latency path a sequence's embedding does not depend on what
+ * else is in the call. */
 int rpx_encoder_set_latency_tokens(rpx_encoder* enc, int32_t max_tokens);
 
 /* T5 bidirectional relative-position bucket of `relative_position` = key - query
