@@ -291,28 +291,27 @@ struct Prof {
 // Latency path: one proof state per call (`retrieve`, retrieval/model.py:348-357, encodes ONE context).
 // With T of a few hundred tokens the 256 x 256 pair tiles of the throughput path leave most of the GPU
 // idle (QKV: 5 tiles, O / FFN-down: 6 tiles on 74 pairs) and every GEMM is bound by the latency of
-// streaming its weights through a handful of SMs.  Here the same contraction core runs 1-CTA tiles of
-// 128 tokens x 64 (FFN-up: 64 or 128) output columns with an 8-deep (6-deep) operand ring: 18-112 CTAs
-// pull the layer's 36 MB of weights in parallel.  K is never split, so every output element is still
-// accumulated over k in the same order as on the throughput path.
+// streaming its operands through a handful of SMs.  Here the same contraction core runs narrow 1-CTA tiles:
+//   up to 384 tokens   QKV, O-proj, FFN-down on 64-ROW tiles (tcgen05.mma M = 64) x 64 columns with a 12-deep
+//                      ring of 16 KB stages: 72 / 92 CTAs for a 200-token state, 138 at 384 tokens (one wave);
+//                      a narrow GEMM's time is its k-blocks times the round trip of the operand ring divided by
+//                      the ring depth, and half-empty 128-row tiles would cost their full intake
+//   beyond             128 x 64 tiles, 8-deep ring (the 64-row tiles would need a second wave: 512 tokens 0.99
+//                      vs 0.59 ms)
+//   FFN-up             128 x 128 tiles = 64 gated hidden units (128 x 64 = 32 units up to 128 tokens), B tile in
+//                      two boxes (gate rows, linear rows)
+// K is never split, so every output element is accumulated over k in the same order whatever the tile, and
+// the residual epilogues write their RMSNorm partial sums per 32-column chunk (n_parts_lat of them) whatever
+// the tile: a state's embedding does not depend on what it was batched with.
+constexpr int kLatBlockN = 64;
+constexpr int kLatStages = 8;
+constexpr int kLatSmallM = 64;
+constexpr int kLatSmallStages = 12;
+constexpr int kLatSmallMMaxTokens = 384;  // 6 row tiles x 23 column tiles = 138 CTAs: the most one wave holds
 // Calls of at most this many tokens run their kernel chain under programmatic dependent launch: at 4 k tokens
 // the re-indexing tiles gain 7 % (2.03 -> 1.89 ms), at 16 k 3-8 %, from 32 k on it is neutral to -1 % (A/B,
 // BASELINE config-5 rows, two runs each).
 constexpr int kPdlMaxTokens = 16384;
-constexpr int kLatBlockN = 64;
-// Up to 384 tokens the QKV projection and the two residual GEMMs (O-proj, FFN down) of the latency path run on
-// 64-ROW tiles (tcgen05.mma M = 64): a narrow GEMM's time is the number of k-blocks times the round trip of
-// its operand ring divided by the ring depth, and a 64 x 64 tile's stage is 16 KB instead of 24 KB — twelve
-// stages instead of eight, and twice the CTAs (72 / 92 for a 200-token state).  Beyond 384 tokens the 64-row
-// tiles no longer fit in one wave (512 tokens: 0.99 vs 0.59 ms) and the 128-row tiles stay.  Both residual variants write their RMSNorm partial sums
-// per 32-column chunk (n_parts_lat of them), so a state's embedding does not depend on what it was batched with.
-constexpr int kLatSmallM = 64;
-constexpr int kLatSmallStages = 12;
-#ifndef RPX_LAT_SMALLM_TOKENS
-#define RPX_LAT_SMALLM_TOKENS 384   // 6 row tiles x 23 column tiles = 138 CTAs: the most one wave holds
-#endif
-constexpr int kLatResMaxTokens = RPX_LAT_SMALLM_TOKENS;
-constexpr int kLatStages = 8;
 
 int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, const void* next_weights,
                           size_t next_bytes, int T, int S, int max_len, cudaStream_t st) {
@@ -324,7 +323,7 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
     EpiStoreBF16::Params ep{ws.qkv, 3 * inner, RowScale{ws.ssA, P, T, inv_d, c.ln_eps}};
     // the QKV projection occupies 18 x ceil(T/64) (or 18 x ceil(T/128)) SMs: the rest of the GPU fetches the
     // next layer's weights into L2
-    if (T <= kLatResMaxTokens) {
+    if (T <= kLatSmallMMaxTokens) {
       RPX_TRY((launch_gemm<kLatBlockN, EpiStoreBF16, false, kLatSmallStages, false, kLatSmallM>(ws.h16, D, w.qkv, D, T, 3 * inner,
                                                                                                  D, ep, st, 0, next_weights,
                                                                                                  next_bytes)));
@@ -341,7 +340,7 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 3);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssB, T};
-    if (T <= kLatResMaxTokens) {
+    if (T <= kLatSmallMMaxTokens) {
       RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatSmallStages, false, kLatSmallM>(ws.attn, inner, w.o, inner, T,
                                                                                                        D, inner, ep, st)));
     } else {
@@ -362,7 +361,7 @@ int forward_latency_layer(rpx_encoder* e, const Workspace& ws, const LayerW& w, 
   {
     Prof p(e, st, 5);
     EpiResidual::Params ep{ws.h32, ws.h16, D, ws.ssA, T};
-    if (T <= kLatResMaxTokens) {
+    if (T <= kLatSmallMMaxTokens) {
       RPX_TRY((launch_gemm<kLatBlockN, EpiResidualT<true>, false, kLatSmallStages, false, kLatSmallM>(ws.ffn, F, w.wo, F, T, D, F,
                                                                                                        ep, st)));
     } else {
