@@ -468,8 +468,20 @@ def retrieve_single_leg(retr, dev):
         prem, sc = retr.retrieve(st, *where, 100)
         lat.append((time.perf_counter() - t0) * 1e3)
     assert len(prem) == 100
+    # where the time goes: the encode of the one state (latency path) alone, CUDA events around the call
+    # (tokenisation, the copy of its bytes and the ~65 launches included)
+    enc_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for st in states[16:48]:
+        torch.cuda.synchronize()
+        e0.record()
+        retr._encode_states([st])
+        e1.record()
+        torch.cuda.synchronize()
+        enc_ms.append(e0.elapsed_time(e1))
     return {"metric": "retrieve() latency, one state per call, host to host", "unit": "ms",
             "median": float(np.median(lat)), "p90": float(np.percentile(lat, 90)), "min": float(min(lat)), "calls": len(lat),
+            "encode_state_ms_median": float(np.median(enc_ms)),
             "config": {"index_rows": N, "files": n_files, "k": 100, "state_bytes": "U[50,400]", "max_seq_len": retr.max_seq_len,
                        "accessible_rows": int(N - N // n_files + 49)}}
 
