@@ -427,7 +427,9 @@ def retrieve_leg(Q, E, handle, k, rank, world, dev, peaks, e0, e1, K, W, check_p
                      "peak": peaks["tf_burst"] if bound == "tensor" else peaks["hbm_gbs"],
                      "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                      "frac": max(t_mma, t_hbm) / (ms_r / 1e3), "hbm_frac": t_hbm / (ms_r / 1e3),
-                     "algorithmic_bytes": bytes_alg, "peak_source": peaks["source"],
+                     # the same against the sustained tensor rate (what a power-capped B200 holds over a step)
+                     "frac_of_sustained": (max(flops / (peaks["tf_sustained"] * 1e12), t_hbm) / (ms_r / 1e3)) if bound == "tensor" else None,
+                     "algorithmic_bytes": bytes_alg, "peak_source": peaks["source"] + (" (burst bf16)" if bound == "tensor" else ""),
                      "note": "whole retrieve (every launch of the call [+ all-gather + merge]) vs max(t_MMA, t_HBM) of one pass over the index"},
     }
     if bound == "hbm" and nq <= 2:
