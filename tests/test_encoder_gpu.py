@@ -166,7 +166,7 @@ def test_byt5_small_full_depth_at_max_seq_len_2048(rpx_lib, cuda_device, out_dir
     assert torch.equal(cut[0], got[3])
 
 
-@pytest.mark.parametrize("n_tok", [1, 17, 128, 129, 300, 700])
+@pytest.mark.parametrize("n_tok", [1, 17, 64, 65, 128, 129, 256, 257, 300, 384, 385, 512, 513, 700, 768, 1024, 1025])
 def test_latency_path_matches_oracle_and_throughput_path(rpx_lib, cuda_device, n_tok):
     """`rpx_encoder_set_latency_tokens`: the narrow-tile kernels used for one proof state per call
     (retrieval/model.py:348-357) against the HF fp32 oracle and against the throughput tiles."""
