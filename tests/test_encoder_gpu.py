@@ -204,6 +204,14 @@ def test_latency_path_batch_equals_single(rpx_lib, cuda_device):
         alone = eng.encode_bytes(np.frombuffer(sbytes, dtype=np.uint8), np.array([0, len(sbytes)], dtype=np.int64), 2048,
                                  out_dtype=torch.float32)
         assert torch.equal(alone[0], together[i]), (i, len(sbytes))
+    # sequences that take one, two and three 256-key attention blocks in the same call
+    parts = [synth.split_strings(*synth.synth_states(1, seed=40 + i, min_len=n, max_len=n))[0] for i, n in enumerate((40, 300, 620))]
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+    mixed = eng.encode_bytes(np.frombuffer(b"".join(parts), dtype=np.uint8), offs, 2048, out_dtype=torch.float32)
+    for i, sbytes in enumerate(parts):
+        alone = eng.encode_bytes(np.frombuffer(sbytes, dtype=np.uint8), np.array([0, len(sbytes)], dtype=np.int64), 2048,
+                                 out_dtype=torch.float32)
+        assert torch.equal(alone[0], mixed[i]), (i, len(sbytes))
     pair = eng.encode_bytes(*synth.synth_states(2, seed=32, min_len=100, max_len=120), 2048, out_dtype=torch.float32)
     d2, o2 = synth.synth_states(2, seed=32, min_len=100, max_len=120)
     for i, sbytes in enumerate(synth.split_strings(d2, o2)):
